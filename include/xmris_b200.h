@@ -1,0 +1,90 @@
+/* xmris_b200 -- C ABI of the B200 FID->spectrum hot path (libxmris_b200.so).
+ *
+ * The reference (andrewendlinger/xmris v0.6.1) is pure Python and has no FFI of its own: its plugin boundary is
+ * the xarray accessor `.xmr` (src/xmris/core/accessor.py:707-710) whose methods forward to the functions in
+ * src/xmris/processing/{fid,fourier,phasing}.py.  Each entry point below names the reference function it
+ * replaces; `xmris_b200/processing.py` is the Python side that binds them with ctypes.
+ *
+ * Conventions
+ *   - complex64 data, interleaved (re, im) float pairs, batch-major: element (b, k) at base[(b*n + k)*2].
+ *     The transform axis is last and contiguous.  Rows must be 8-byte aligned; the TMA (bulk-copy) fast path is
+ *     taken when the base pointer is 16-byte aligned and n_in is even, otherwise a plain-load path is used.
+ *   - `*_dev` pointers are caller-owned DEVICE memory on the current CUDA device; `*_host` are host memory.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream) unless it
+ *     says otherwise.  No hidden allocation except a per-(device, N) twiddle-table cache guarded by a mutex.
+ *   - return value: 0 on success, else one of XMR_ERR_*; xmr_last_error() returns the thread-local message.
+ *   - supported transform lengths n_out: powers of two in [16, 8192] (one spectrum per CTA-resident slot).
+ */
+#ifndef XMRIS_B200_H
+#define XMRIS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XMR_OK 0
+#define XMR_ERR_BAD_ARG 1        /* NULL pointer, negative size, n_in > n_out, bad pad_left ...            */
+#define XMR_ERR_UNSUPPORTED_N 2  /* n_out is not a power of two in [16, 8192]                              */
+#define XMR_ERR_CUDA 3           /* a CUDA runtime call failed; message holds cudaGetErrorString           */
+#define XMR_ERR_NO_CONVERGE 4    /* reserved                                                               */
+
+/* window_mode */
+#define XMR_WIN_NONE 0      /* multiply by `scale` only                                                    */
+#define XMR_WIN_TABLE 1     /* window_dev[k], k < n_out  (already includes any 1/sqrt(N))                  */
+#define XMR_WIN_SEPARABLE 2 /* w[M*n1 + n2] = window_dev[n2] * win_rows_host[n1], M = min(n_out, 256)      */
+
+/* phase_mode of the fused epilogue */
+#define XMR_PHASE_NONE 0
+#define XMR_PHASE_UNIFORM 1 /* out[b,m] *= exp(2*pi*i*(ph_a_turns + ph_b_turns*m)), same for every spectrum */
+
+/* autophase objective (src/xmris/processing/phasing.py:100-157) */
+#define XMR_METHOD_ACME 0
+#define XMR_METHOD_PEAK_MINIMA 1
+#define XMR_METHOD_POSITIVITY 2
+
+int xmr_version(void);
+const char* xmr_last_error(void);
+
+/* Fused zero_fill -> apodize -> FFT(ortho via the window scale) -> fftshift [-> uniform phase].
+ * Replaces: zero_fill   src/xmris/processing/fid.py:201-285  (implicit: padded points never touch HBM)
+ *           apodize_exp src/xmris/processing/fid.py:105-144  (window table / separable window)
+ *           to_spectrum src/xmris/processing/fid.py:9-42 = fft (fourier.py:117-173) + fftshift (fourier.py:10-32)
+ *           phase       src/xmris/processing/phasing.py:56-73 (optional epilogue, uniform coordinates)
+ * Also serves to_fid (fid.py:45-102) with inverse=1, in_shift=(n+1)/2, out_shift=0.
+ *
+ *   fid_dev   [batch, n_in] complex64      spec_dev [batch, n_out] complex64 (may be NULL: statistics only)
+ *   pad_left  zeros before the data ("symmetric" position: (n_out-n_in)/2; "end": 0)
+ *   in_shift  input index rotation: x[k] is read from fid[(k + in_shift) mod n_in]; requires n_in == n_out
+ *   out_shift output index rotation: bin j is stored at (j + out_shift) mod n_out  (n_out/2 = fftshift)
+ *   absmax_dev/argmax_dev  optional [batch]: max |S| (float) and its first index (in stored order) per spectrum
+ */
+int xmr_fid_to_spectrum_c64(const void* fid_dev, void* spec_dev, int64_t batch, int n_in, int n_out, int pad_left,
+                            int window_mode, const float* window_dev, const float* win_rows_host, float scale,
+                            int inverse, int in_shift, int out_shift, float* absmax_dev, int* argmax_dev,
+                            int phase_mode, double ph_a_turns, double ph_b_turns, void* stream);
+
+/* Standalone elementwise ops for the un-fused accessor calls.
+ * xmr_zero_fill_c64  replaces zero_fill   (fid.py:251)  out[b, pad_left + k] = in[b, k], zeros elsewhere
+ * xmr_scale_rows_c64 replaces apodize_exp (fid.py:139)  out[b, k] = in[b, k] * w_dev[k]          (real weights)
+ * xmr_rotate_rows_c64 replaces phase      (phasing.py:73) out[b, k] = in[b, k] * rot_dev[k]      (complex weights)
+ */
+int xmr_zero_fill_c64(const void* in_dev, void* out_dev, int64_t batch, int n_in, int n_out, int pad_left,
+                      void* stream);
+int xmr_scale_rows_c64(const void* in_dev, void* out_dev, int64_t batch, int n, const float* w_dev, void* stream);
+int xmr_rotate_rows_c64(const void* in_dev, void* out_dev, int64_t batch, int n, const void* rot_dev, void* stream);
+
+/* Per-spectrum phase: out[b,m] = in[b,m] * exp(2*pi*i*(a_turns[b] + b_turns[b]*m)).  (phasing.py:56-73 per voxel) */
+int xmr_phase_each_c64(const void* in_dev, void* out_dev, int64_t batch, int n, const double* a_turns_dev,
+                       const double* b_turns_dev, void* stream);
+
+/* Global first-occurrence argmax over a [batch] array of per-spectrum maxima (phasing.py:229-231).
+ * Writes {max value, flat index = spectrum*n + argmax[spectrum]} to out_dev (float, then int64 at byte offset 8). */
+int xmr_global_argmax(const float* absmax_dev, const int* argmax_dev, int64_t batch, int n, void* out_dev,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XMRIS_B200_H */

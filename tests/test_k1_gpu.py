@@ -1,0 +1,167 @@
+"""GPU parity tests of K1 (fused zero-fill -> window -> FFT -> fftshift [-> stats] [-> phase]) against the oracle.
+
+Tolerance: north_star states spectra within 1e-5 relative L2 (complex64 device vs the reference's complex128).
+"""
+
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+from oracle import xmris_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+
+    assert torch.cuda.is_available()
+    from xmris_b200 import _lib
+
+    _lib.load()  # fail loudly if the CUDA library is not built
+    return torch.device("cuda:0")
+
+
+def _rand(rng, shape):
+    return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+
+
+@pytest.mark.parametrize("n_out", [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+def test_plain_fft_all_lengths(dev, n_out):
+    import torch
+    from xmris_b200 import device as D
+
+    rng = np.random.default_rng(n_out)
+    for batch in (1, 3, 70, 301):
+        x = _rand(rng, (batch, n_out))
+        t = np.arange(n_out) * 1e-3
+        spec, _, _ = D.fid_to_spectrum(torch.from_numpy(x).to(dev))
+        ref, _ = orc.to_spectrum(x.astype(np.complex128), 1, t)
+        got = spec.cpu().numpy()
+        errs = [rel_l2(got[i], ref[i]) for i in range(batch)]
+        assert max(errs) < TOL, (n_out, batch, max(errs))
+
+
+@pytest.mark.parametrize("n_in,n_out,position", [(1024, 2048, "end"), (4096, 8192, "end"), (64, 512, "end"),
+                                                   (32, 128, "symmetric"), (1000, 4096, "symmetric"),
+                                                   (1023, 2048, "end"), (37, 64, "symmetric"), (2048, 2048, "end")])
+def test_chain_zero_fill_window(dev, n_in, n_out, position):
+    import torch
+    from xmris_b200 import device as D
+
+    rng = np.random.default_rng(n_in * 7 + n_out)
+    batch = 37
+    x = _rand(rng, (batch, n_in))
+    t = 2e-4 * np.arange(n_in)
+    lb = 5.0
+    ref, freqs = orc.chain_to_spectrum(x.astype(np.complex128), 1, t, n_out if n_out > n_in else None, position, lb)
+    # host-side metadata exactly as the product computes it
+    _, t_pad, _ = orc.zero_fill(np.zeros(n_in), 0, t, n_out, position)
+    pad_left = 0 if position == "end" else (n_out - n_in) // 2
+    w = np.exp(-np.pi * lb * t_pad) / np.sqrt(n_out)
+    spec, amax, imax = D.fid_to_spectrum(torch.from_numpy(x).to(dev), n_out=n_out, pad_left=pad_left, window=w,
+                                         want_stats=True)
+    got = spec.cpu().numpy()
+    errs = [rel_l2(got[i], ref[i]) for i in range(batch)]
+    assert max(errs) < TOL, max(errs)
+    # statistics: max |S| and its first index per spectrum
+    ref_abs = np.abs(ref)
+    np.testing.assert_allclose(amax.cpu().numpy(), ref_abs.max(axis=1), rtol=2e-5)
+    gi = imax.cpu().numpy()
+    for i in range(batch):
+        assert ref_abs[i, gi[i]] >= ref_abs[i].max() * (1 - 2e-5)
+
+
+def test_non_separable_window_table(dev):
+    import torch
+    from xmris_b200 import device as D
+
+    rng = np.random.default_rng(5)
+    n = 4096
+    x = _rand(rng, (19, n))
+    w = rng.uniform(0.2, 1.0, n)   # arbitrary (non-uniform time axis) window -> full table path
+    spec, _, _ = D.fid_to_spectrum(torch.from_numpy(x).to(dev), window=w / np.sqrt(n))
+    ref = np.roll(np.fft.fft(x.astype(np.complex128) * w, axis=1, norm="ortho"), n // 2, axis=1)
+    assert rel_l2(spec.cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("n", [256, 1024, 4096, 8192])
+def test_fused_uniform_phase(dev, n):
+    import torch
+    from xmris_b200 import device as D
+
+    rng = np.random.default_rng(n + 1)
+    x = _rand(rng, (23, n))
+    t = np.arange(n) / 5000.0
+    ref, freqs = orc.to_spectrum(x.astype(np.complex128), 1, t)
+    p0, p1, pivot = -137.25, 2891.5, float(freqs[n // 3])
+    refp, _ = orc.phase(ref, 1, freqs, p0, p1, pivot)
+    df = freqs[1] - freqs[0]
+    rng_ = freqs.max() - freqs.min()
+    b = (p1 / 360.0) * df / rng_
+    a = p0 / 360.0 + (p1 / 360.0) * (freqs[0] - pivot) / rng_
+    spec, _, _ = D.fid_to_spectrum(torch.from_numpy(x).to(dev), phase_turns=(a, b))
+    assert rel_l2(spec.cpu().numpy(), refp) < TOL
+
+
+@pytest.mark.parametrize("n", [64, 256, 2048, 4096])
+def test_inverse_round_trip(dev, n):
+    import torch
+    from xmris_b200 import device as D
+
+    rng = np.random.default_rng(n + 2)
+    x = _rand(rng, (11, n))
+    t = np.arange(n) / 4000.0
+    xd = torch.from_numpy(x).to(dev)
+    spec, _, _ = D.fid_to_spectrum(xd)
+    back, _, _ = D.fid_to_spectrum(spec, inverse=True, in_shift=n // 2, out_shift=0)
+    ref_spec, freqs = orc.to_spectrum(x.astype(np.complex128), 1, t)
+    ref_back, _ = orc.to_fid(ref_spec, 1, freqs)
+    assert rel_l2(back.cpu().numpy(), ref_back) < TOL
+    assert rel_l2(back.cpu().numpy(), x) < TOL
+
+
+def test_elementwise_ops(dev):
+    import torch
+    from xmris_b200 import device as D
+
+    rng = np.random.default_rng(9)
+    x = _rand(rng, (13, 300))
+    xd = torch.from_numpy(x).to(dev)
+    z = D.zero_fill(xd, 777, pad_left=100).cpu().numpy()
+    ref = np.zeros((13, 777), np.complex64)
+    ref[:, 100:400] = x
+    np.testing.assert_array_equal(z, ref)
+    w = rng.uniform(0, 1, 300)
+    np.testing.assert_allclose(D.scale_rows(xd, w).cpu().numpy(), x * w.astype(np.float32), rtol=1e-6)
+    rot = np.exp(1j * rng.uniform(-3, 3, 300))
+    assert rel_l2(D.rotate_rows(xd, rot).cpu().numpy(), x * rot) < 1e-6
+    a = torch.from_numpy(rng.uniform(-1, 1, 13)).to(dev)
+    b = torch.from_numpy(rng.uniform(-0.01, 0.01, 13)).to(dev)
+    got = D.phase_each(xd, a, b).cpu().numpy()
+    refp = x * np.exp(2j * np.pi * (a.cpu().numpy()[:, None] + b.cpu().numpy()[:, None] * np.arange(300)[None, :]))
+    assert rel_l2(got, refp) < 2e-6
+
+
+def test_global_argmax_first_occurrence(dev):
+    import torch
+    from xmris_b200 import device as D
+
+    v = np.array([1.0, 5.0, 3.0, 5.0, 2.0], np.float32)
+    i = np.array([7, 11, 2, 1, 0], np.int32)
+    val, flat = D.global_argmax(torch.from_numpy(v).to(dev), torch.from_numpy(i).to(dev), 100)
+    assert val == 5.0 and flat == 1 * 100 + 11
+
+
+def test_errors(dev):
+    import torch
+    from xmris_b200 import device as D
+
+    x = torch.zeros((2, 1972), dtype=torch.complex64, device=dev)
+    with pytest.raises(ValueError, match="not supported"):
+        D.fid_to_spectrum(x)
+    with pytest.raises(TypeError):
+        D.fid_to_spectrum(torch.zeros((2, 64), dtype=torch.complex64))

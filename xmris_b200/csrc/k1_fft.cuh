@@ -1,0 +1,238 @@
+// K1: fused  zero-fill -> window -> FFT -> fftshift [-> |S| statistics] [-> uniform phase] -> store.
+//
+// One persistent CTA loops over "tiles" of SPB consecutive spectra.  Per tile:
+//   producer (thread 0)   cp.async.bulk global->shared of the raw FID rows into ring slot (it % STAGES),
+//                         completion on an mbarrier (TMA bulk-copy engine; SASS UBLKCP)
+//   all threads           wait(mbarrier) -> stage0 (in-place exchange A) -> bar -> stage1 (exchange B) -> bar
+//                         -> [producer re-arms the slot for tile it+STAGES] -> stage2 -> epilogue from registers
+// Padded points are never read or written in HBM; the shifted store index implements fftshift.
+// HBM traffic per spectrum = 8*n_in + 8*n_out bytes (+8 B of statistics), the algorithmic minimum.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fft_stages.cuh"
+#include "ptx_sm100.cuh"
+
+namespace xmr {
+
+constexpr int K1_STAGES = 2;
+
+
+struct K1Params {
+    const float2* in;
+    float2* out;
+    long long batch;
+    int n_in;
+    int pad_left;
+    int in_shift;
+    int out_shift;
+    float scale;
+    const float2* twN;     // exp(-2 pi i k / N), k < N
+    const float* win;      // table [N] (WIN==1) or column factors [min(N,256)] (WIN==2)
+    float win_rows[32];    // row factors (WIN==2)
+    float* absmax;
+    int* argmax;
+    int phase_on;          // epilogue: multiply by exp(2 pi i (a + b*m)), m = stored index
+    double ph_a_turns;     // uniform phase: turns(m) = a + b*m
+    double ph_b_turns;
+    float2 ph_step[16];    // exp(2 pi i * b * R0*R1 * d), d < 16
+};
+
+template <int N>
+struct K1Smem {
+    using C = FftCfg<N>;
+    static constexpr size_t RING = size_t(K1_STAGES) * C::SPB * C::N * sizeof(float2);
+    static constexpr size_t B = size_t(C::SPB) * C::SIZE_B * sizeof(float2);
+    static constexpr size_t RED = size_t(C::SPB) * 32 * 8;  // per group: up to 32 warps x (float, int)
+    static constexpr size_t BAR = 64;
+    static constexpr size_t TOTAL = RING + B + RED + BAR;
+};
+
+template <int N>
+constexpr int k1_min_blocks() {
+    // shared-memory limited residency on a 227 KB SM, capped at 2048 threads and at 3 CTAs
+    int by_smem = int((227u * 1024u) / (K1Smem<N>::TOTAL + 1024));
+    int by_thr = 2048 / FftCfg<N>::THREADS;
+    int m = by_smem < by_thr ? by_smem : by_thr;
+    if (m > 2) m = 2;   // persistent per-thread twiddles want <= 128 registers/thread at 256 threads
+    return m < 1 ? 1 : m;
+}
+
+// (value, index) max-reduction with first-occurrence tie-break
+__device__ __forceinline__ void amax_combine(float& v, int& i, float ov, int oi) {
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+}
+
+// WIN: 1 = full window table p.win[N]; 2 = separable p.win[column] * p.win_rows[row] (also "scale only").
+// The epilogue options (statistics, phase, store) are uniform run-time flags: p.absmax, p.phase_on, p.out.
+template <int N, bool INVERSE, int WIN, bool TMA>
+__global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_kernel(const __grid_constant__ K1Params p) {
+    using C = FftCfg<N>;
+    constexpr bool TW_PERSIST = (N <= 4096);
+    constexpr int NTW = (C::R0 > 1) ? C::C0 * (C::R0 - 1) : 1;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* ring = reinterpret_cast<float2*>(smem_raw);
+    float2* Bbuf = reinterpret_cast<float2*>(smem_raw + K1Smem<N>::RING);
+    float* red = reinterpret_cast<float*>(smem_raw + K1Smem<N>::RING + K1Smem<N>::B);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + K1Smem<N>::RING + K1Smem<N>::B + K1Smem<N>::RED);
+
+    const int tid = threadIdx.x;
+    const int g = tid / C::T;     // spectrum slot within the tile
+    const int t = tid % C::T;     // thread within the spectrum
+
+    const long long ntiles = (p.batch + C::SPB - 1) / C::SPB;
+    const int n_in = p.n_in;
+    const bool need_load_barrier = (p.pad_left != 0) || ((p.in_shift % C::M) != 0);
+
+    // ---- per-thread persistent state -------------------------------------------------------------------
+    float2 tw_persist[TW_PERSIST ? NTW : 1];
+    float2 tw0_base[C::C0 * 2], tw1_base[C::C1 * 2];
+    init_twiddles<C, INVERSE>(t, p.twN, TW_PERSIST ? tw_persist : nullptr, tw0_base, tw1_base);
+    float wcol[C::C0];
+    if (WIN == 2) {
+#pragma unroll
+        for (int j = 0; j < C::C0; ++j) wcol[j] = p.win ? p.win[t + C::T * j] : p.scale;   // null: scale only
+    }
+    float2 ph_base[C::C2];
+#pragma unroll
+    for (int j = 0; j < C::C2; ++j) ph_base[j] = make_float2(1.f, 0.f);
+    if (p.phase_on) {
+#pragma unroll
+        for (int j = 0; j < C::C2; ++j) {
+            const int q = t + C::T * j;
+            double turns = p.ph_a_turns + p.ph_b_turns * double(q);
+            turns -= floor(turns);
+            double s, c;
+            sincospi(2.0 * turns, &s, &c);
+            ph_base[j] = make_float2(float(c), float(s));
+        }
+    }
+
+    auto issue = [&](long long tile, int slot) {
+        // producer: arm the barrier with the tile's byte count, then one bulk copy per spectrum row
+        const long long s0 = tile * C::SPB;
+        const int nvalid = int((p.batch - s0) < C::SPB ? (p.batch - s0) : C::SPB);
+        const uint32_t row_bytes = uint32_t(n_in) * 8u;
+        mbar_arrive_expect_tx(&bars[slot], row_bytes * nvalid);
+        float2* dst = ring + size_t(slot) * C::SPB * C::N;
+        if (n_in == C::N) {
+            bulk_g2s(dst, p.in + s0 * n_in, row_bytes * nvalid, &bars[slot]);
+        } else {
+            for (int r = 0; r < nvalid; ++r) bulk_g2s(dst + size_t(r) * C::N, p.in + (s0 + r) * n_in, row_bytes, &bars[slot]);
+        }
+    };
+
+    if (TMA) {
+        if (tid == 0) {
+            for (int s = 0; s < K1_STAGES; ++s) mbar_init(&bars[s], 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int s = 0; s < K1_STAGES; ++s) {
+                const long long tile = blockIdx.x + (long long)s * gridDim.x;
+                if (tile < ntiles) issue(tile, s);
+            }
+        }
+    }
+
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int slot = it % K1_STAGES;
+        const long long spec = tile * C::SPB + g;
+        const bool valid = spec < p.batch;
+        float2* my_slot = ring + (size_t(slot) * C::SPB + g) * C::N;
+        float2* my_B = Bbuf + size_t(g) * C::SIZE_B;
+
+        if (TMA) {
+            mbar_wait(&bars[slot], (it / K1_STAGES) & 1);
+        } else {
+            // plain-load path (unaligned base or odd n_in): cooperative coalesced copy of the tile's rows
+            const long long s0 = tile * C::SPB;
+            const int nvalid = int((p.batch - s0) < C::SPB ? (p.batch - s0) : C::SPB);
+            __syncthreads();   // previous tile's readers of this slot are done
+            for (int idx = tid; idx < nvalid * n_in; idx += C::THREADS) {
+                const int r = idx / n_in, k = idx - r * n_in;
+                ring[(size_t(slot) * C::SPB + r) * C::N + k] = p.in[(s0 + r) * n_in + k];
+            }
+            __syncthreads();
+        }
+
+        // ---- stage 0: load (zero-fill + window), R0-point DFTs, in-place exchange A --------------------
+        float2 v[C::E];
+        stage0_load<C, WIN>(t, my_slot, valid ? n_in : 0, p.pad_left, p.in_shift, p.scale, p.win, wcol, p.win_rows, v);
+        if (need_load_barrier) __syncthreads();
+        stage0_store<C, INVERSE, TW_PERSIST>(t, my_slot, v, tw_persist, tw0_base);
+        __syncthreads();
+        // ---- stage 1: R1-point DFTs, exchange B ----------------------------------------------------------
+        stage1<C, INVERSE>(t, my_slot, my_B, tw1_base);
+        __syncthreads();
+        // the input slot is free again: prefetch tile it+STAGES into it while stage 2 and the epilogue run
+        if (TMA && tid == 0) {
+            const long long nt = tile + (long long)K1_STAGES * gridDim.x;
+            if (nt < ntiles) {
+                fence_proxy_async_smem();
+                issue(nt, slot);
+            }
+        }
+        // ---- stage 2: R2-point DFTs, results in registers ------------------------------------------------
+        stage2<C, INVERSE>(t, my_B, v);
+
+        // ---- epilogue --------------------------------------------------------------------------------------
+        constexpr int Q = C::R0 * C::R1;
+        if (p.absmax != nullptr) {
+            float best = -1.f;
+            int besti = 0x7fffffff;
+#pragma unroll
+            for (int j = 0; j < C::C2; ++j)
+#pragma unroll
+                for (int d = 0; d < C::R2; ++d) {
+                    const float2 x = v[j * C::R2 + d];
+                    const float m2 = x.x * x.x + x.y * x.y;
+                    const int m = (t + C::T * j + Q * d + p.out_shift) & (C::N - 1);
+                    amax_combine(best, besti, m2, m);
+                }
+            constexpr int LANES = C::T < 32 ? C::T : 32;
+#pragma unroll
+            for (int off = LANES / 2; off > 0; off >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, besti, off);
+                amax_combine(best, besti, ov, oi);
+            }
+            if (C::T > 32) {
+                constexpr int WPG = C::T / 32;
+                float* rv = red + size_t(g) * 64;
+                int* ri = reinterpret_cast<int*>(rv) + 32;
+                if ((t & 31) == 0) { rv[t >> 5] = best; ri[t >> 5] = besti; }
+                __syncthreads();
+                if (t == 0) {
+                    for (int w = 1; w < WPG; ++w) amax_combine(best, besti, rv[w], ri[w]);
+                }
+            }
+            if (t == 0 && valid) {
+                p.absmax[spec] = sqrtf(best);
+                p.argmax[spec] = besti;
+            }
+        }
+        if (p.out != nullptr && valid) {
+            float2* dst = p.out + spec * (long long)C::N;
+#pragma unroll
+            for (int j = 0; j < C::C2; ++j)
+#pragma unroll
+                for (int d = 0; d < C::R2; ++d) {
+                    const int k = t + C::T * j + Q * d;
+                    const int m = (k + p.out_shift) & (C::N - 1);
+                    float2 x = v[j * C::R2 + d];
+                    if (p.phase_on) {
+                        // m = q + Q*d' with d' = m / Q: rot = base(q) * step(d')
+                        const float2 r = cmul(ph_base[j], p.ph_step[(m / Q) & 15]);
+                        x = cmul(x, r);
+                    }
+                    st_stream(dst + m, x);
+                }
+        }
+    }
+}
+
+}  // namespace xmr

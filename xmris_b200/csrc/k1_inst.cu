@@ -1,0 +1,54 @@
+// One instantiation set of K1 per transform length: compile with -DXMR_N=<N>.
+#include "k1_launch.cuh"
+
+#ifndef XMR_N
+#error "compile with -DXMR_N=<transform length>"
+#endif
+
+namespace xmr {
+
+template <int N, bool INVERSE, int WIN, bool TMA>
+static cudaError_t launch_one(const K1Params& p, int max_ctas, cudaStream_t st) {
+    using C = FftCfg<N>;
+    auto kern = k1_kernel<N, INVERSE, WIN, TMA>;
+    constexpr size_t smem = K1Smem<N>::TOTAL;
+    static thread_local int cached_dev = -1;
+    static thread_local int ctas_per_wave = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev != cached_dev) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        int per_sm = 0, sms = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        ctas_per_wave = per_sm * sms;
+        cached_dev = dev;
+    }
+    const long long ntiles = (p.batch + C::SPB - 1) / C::SPB;
+    long long grid = ntiles < ctas_per_wave ? ntiles : ctas_per_wave;
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    if (grid < 1) return cudaSuccess;
+    kern<<<dim3((unsigned)grid), dim3(C::THREADS), smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+#define XMR_CAT2(a, b) a##b
+#define XMR_CAT(a, b) XMR_CAT2(a, b)
+
+cudaError_t XMR_CAT(k1_launch_, XMR_N)(const K1Params& p, bool inverse, int win, bool tma, int max_ctas,
+                                       cudaStream_t st) {
+    if (inverse) {
+        // to_fid: no window (scale only -> separable mode with unit rows)
+        return tma ? launch_one<XMR_N, true, 2, true>(p, max_ctas, st) : launch_one<XMR_N, true, 2, false>(p, max_ctas, st);
+    }
+    if (win == 1)
+        return tma ? launch_one<XMR_N, false, 1, true>(p, max_ctas, st) : launch_one<XMR_N, false, 1, false>(p, max_ctas, st);
+    return tma ? launch_one<XMR_N, false, 2, true>(p, max_ctas, st) : launch_one<XMR_N, false, 2, false>(p, max_ctas, st);
+}
+
+}  // namespace xmr

@@ -1,0 +1,217 @@
+"""Array-level API on device-resident torch tensors -> C ABI (``libxmris_b200.so``).
+
+Everything here takes / returns ``torch`` CUDA tensors (complex64, transform axis last, contiguous) and plain
+numpy/float metadata.  torch is plumbing only (device memory, streams); all arithmetic happens in the
+hand-written sm_100a kernels behind the C ABI.  There is no CPU fallback: a missing library or a CPU tensor
+raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+
+from . import _lib
+
+SUPPORTED_N = tuple(2**k for k in range(4, 14))  # 16 .. 8192
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _require_cuda(x, name):
+    torch = _torch()
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise TypeError(f"{name} must be a CUDA torch tensor (xmris_b200 has no CPU path)")
+    if x.dtype != torch.complex64:
+        raise TypeError(f"{name} must be complex64, got {x.dtype}")
+    if not x.is_contiguous():
+        raise ValueError(f"{name} must be contiguous with the transform axis last")
+
+
+def _stream_ptr(stream=None):
+    torch = _torch()
+    s = torch.cuda.current_stream() if stream is None else stream
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def check_length(n_out: int):
+    if n_out not in SUPPORTED_N:
+        raise ValueError(
+            f"xmris_b200: transform length {n_out} is not supported (powers of two in [16, 8192]); "
+            "there is no CPU fallback"
+        )
+
+
+# ---------------------------------------------------------------------------------------------------------
+# windows
+# ---------------------------------------------------------------------------------------------------------
+
+
+def split_window(w: np.ndarray, n_out: int):
+    """Factor a float64 window ``w[n_out]`` as ``cols[n2] * rows[n1]`` (n = M*n1 + n2, M = min(n_out, 256)).
+
+    Exponential windows on a uniform time axis factor exactly (``apodize_exp``, ``fid.py:132-136``); anything else
+    falls back to the full table.  Returns ``(mode, table_float32, rows_float32_or_None)``.
+    """
+    w = np.asarray(w, dtype=np.float64)
+    if w.shape != (n_out,):
+        raise ValueError(f"window must have shape ({n_out},), got {w.shape}")
+    m = min(n_out, 256)
+    r0 = n_out // m
+    if r0 == 1:
+        return _lib.WIN_SEPARABLE, w.astype(np.float32), np.ones(1, np.float32)
+    if w[0] != 0.0 and np.all(np.isfinite(w)):
+        cols = w[:m]
+        rows = w[::m] / w[0]
+        recon = (rows[:, None] * cols[None, :]).ravel()
+        if np.allclose(recon, w, rtol=1e-9, atol=1e-300):
+            return _lib.WIN_SEPARABLE, cols.astype(np.float32), rows.astype(np.float32)
+    return _lib.WIN_TABLE, w.astype(np.float32), None
+
+
+# ---------------------------------------------------------------------------------------------------------
+# K1: fused FID -> spectrum
+# ---------------------------------------------------------------------------------------------------------
+
+
+def fid_to_spectrum(fid, n_out=None, pad_left=0, window=None, scale=None, inverse=False, in_shift=0, out_shift=None,
+                    want_stats=False, phase_turns=None, out=None, store=True, stream=None):
+    """Fused zero-fill -> window -> FFT -> shift [-> phase] on the device.
+
+    fid          complex64 CUDA tensor ``[..., n_in]``
+    n_out        transform length (>= n_in); zero filling is implicit
+    window       float64 numpy ``[n_out]`` multiplied before the transform (should include ``1/sqrt(n_out)`` for the
+                 reference's ortho norm); ``None`` -> multiply by ``scale`` (default ``1/sqrt(n_out)``)
+    out_shift    index rotation of the stored bins; default ``n_out//2`` (= fftshift, ``fourier.py:31-32``)
+    phase_turns  ``(a, b)``: multiply stored bin m by ``exp(2 pi i (a + b m))``
+    Returns ``(spectrum or None, absmax or None, argmax or None)``.
+    """
+    torch = _torch()
+    lib = _lib.load()
+    _require_cuda(fid, "fid")
+    n_in = fid.shape[-1]
+    n_out = n_in if n_out is None else int(n_out)
+    check_length(n_out)
+    batch_shape = tuple(fid.shape[:-1])
+    batch = int(np.prod(batch_shape)) if batch_shape else 1
+    if out_shift is None:
+        out_shift = n_out // 2
+    if scale is None:
+        scale = 1.0 / math.sqrt(n_out)
+    dev = fid.device
+    spec = None
+    if store:
+        if out is None:
+            spec = torch.empty(batch_shape + (n_out,), dtype=torch.complex64, device=dev)
+        else:
+            _require_cuda(out, "out")
+            if tuple(out.shape) != batch_shape + (n_out,):
+                raise ValueError("out has the wrong shape")
+            spec = out
+    absmax = argmax = None
+    if want_stats:
+        absmax = torch.empty(batch_shape, dtype=torch.float32, device=dev)
+        argmax = torch.empty(batch_shape, dtype=torch.int32, device=dev)
+    win_mode, win_dev, rows = _lib.WIN_NONE, None, None
+    if window is not None:
+        win_mode, table, rows = split_window(window, n_out)
+        win_dev = torch.from_numpy(np.ascontiguousarray(table)).to(dev)
+    rows_arr = (ctypes.c_float * 32)(*([1.0] * 32))
+    if rows is not None:
+        for i, r in enumerate(rows):
+            rows_arr[i] = float(r)
+    pa, pb = (0.0, 0.0) if phase_turns is None else (float(phase_turns[0]), float(phase_turns[1]))
+    with torch.cuda.device(dev):
+        rc = lib.xmr_fid_to_spectrum_c64(
+            _ptr(fid), _ptr(spec), batch, n_in, n_out, int(pad_left), win_mode, _ptr(win_dev),
+            ctypes.cast(rows_arr, ctypes.c_void_p), ctypes.c_float(scale), int(bool(inverse)), int(in_shift),
+            int(out_shift), _ptr(absmax), _ptr(argmax),
+            _lib.PHASE_NONE if phase_turns is None else _lib.PHASE_UNIFORM, pa, pb, _stream_ptr(stream))
+    _lib.check(rc)
+    return spec, absmax, argmax
+
+
+# ---------------------------------------------------------------------------------------------------------
+# un-fused elementwise pieces (each accessor call on its own)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def zero_fill(x, n_out, pad_left=0, stream=None):
+    torch = _torch()
+    lib = _lib.load()
+    _require_cuda(x, "x")
+    n_in = x.shape[-1]
+    batch = x.numel() // max(n_in, 1)
+    out = torch.empty(tuple(x.shape[:-1]) + (n_out,), dtype=torch.complex64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.xmr_zero_fill_c64(_ptr(x), _ptr(out), batch, n_in, n_out, int(pad_left), _stream_ptr(stream)))
+    return out
+
+
+def scale_rows(x, weights, stream=None):
+    """``x * weights`` along the last axis; ``weights`` float64 numpy (rounded to float32 on upload)."""
+    torch = _torch()
+    lib = _lib.load()
+    _require_cuda(x, "x")
+    n = x.shape[-1]
+    w = torch.from_numpy(np.ascontiguousarray(np.asarray(weights, dtype=np.float64).astype(np.float32))).to(x.device)
+    if w.shape != (n,):
+        raise ValueError("weights must match the last axis")
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.xmr_scale_rows_c64(_ptr(x), _ptr(out), x.numel() // max(n, 1), n, _ptr(w), _stream_ptr(stream)))
+    return out
+
+
+def rotate_rows(x, rot, stream=None):
+    """``x * rot`` along the last axis; ``rot`` complex128 numpy of unit phasors (rounded to complex64)."""
+    torch = _torch()
+    lib = _lib.load()
+    _require_cuda(x, "x")
+    n = x.shape[-1]
+    r = torch.from_numpy(np.ascontiguousarray(np.asarray(rot, dtype=np.complex128).astype(np.complex64))).to(x.device)
+    if r.shape != (n,):
+        raise ValueError("rot must match the last axis")
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.xmr_rotate_rows_c64(_ptr(x), _ptr(out), x.numel() // max(n, 1), n, _ptr(r), _stream_ptr(stream)))
+    return out
+
+
+def phase_each(x, a_turns, b_turns, stream=None):
+    """Per-spectrum phase: ``x[b, m] * exp(2 pi i (a_turns[b] + b_turns[b] m))`` (float64 CUDA tensors [batch])."""
+    torch = _torch()
+    lib = _lib.load()
+    _require_cuda(x, "x")
+    n = x.shape[-1]
+    batch = x.numel() // max(n, 1)
+    a = a_turns.to(device=x.device, dtype=torch.float64).contiguous().reshape(-1)
+    b = b_turns.to(device=x.device, dtype=torch.float64).contiguous().reshape(-1)
+    if a.numel() != batch or b.numel() != batch:
+        raise ValueError("a_turns / b_turns must have one entry per spectrum")
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.xmr_phase_each_c64(_ptr(x), _ptr(out), batch, n, _ptr(a), _ptr(b), _stream_ptr(stream)))
+    return out
+
+
+def global_argmax(absmax, argmax, n, stream=None):
+    """First-occurrence global argmax over per-spectrum maxima.  Returns ``(max_value, flat_index)`` (host sync)."""
+    torch = _torch()
+    lib = _lib.load()
+    out = torch.zeros(16, dtype=torch.uint8, device=absmax.device)
+    with torch.cuda.device(absmax.device):
+        _lib.check(lib.xmr_global_argmax(_ptr(absmax), _ptr(argmax), absmax.numel(), int(n), _ptr(out),
+                                         _stream_ptr(stream)))
+    host = out.cpu().numpy()
+    return float(host[:4].view(np.float32)[0]), int(host[8:16].view(np.int64)[0])
