@@ -84,6 +84,23 @@ int xmr_phase_each_c64(const void* in_dev, void* out_dev, int64_t batch, int n, 
 int xmr_global_argmax(const float* absmax_dev, const int* argmax_dev, int64_t batch, int n, void* out_dev,
                       void* stream);
 
+/* Per-row statistics of an existing spectrum array: max |S| and its first index (numpy argmax order),
+ * the first step of autophase / phase(pivot=None)  (phasing.py:49-53, 229-231). */
+int xmr_row_absmax_c64(const void* spec_dev, int64_t batch, int n, float* absmax_dev, int* argmax_dev, void* stream);
+
+/* autophase(mode="single") optimiser on ONE spectrum.  Replaces the scipy.optimize.differential_evolution call of
+ * src/xmris/processing/phasing.py:270-287 (bounds p0 in [-180,180], p1 in [-4000,4000]; p0_only -> p1 = 0) by a
+ * deterministic dense grid (float32) + nested float64 zoom refinement of the reference's objective
+ * (method: ACME phasing.py:100-122, peak_minima :125-139, positivity :142-157).
+ *   u0, du        u_m = u0 + du*m = (x_m - pivot)/(x_max - x_min)  -- the reference's phase ramp (phasing.py:56-69)
+ *   target_idx, index_width   ROI of the local methods (phasing.py:233-247)
+ *   result_dev    double[4] on the device: {p0 deg, p1 deg, objective value, 0}
+ *   workspace_dev at least xmr_autophase_workspace_bytes() bytes of device memory, caller-owned
+ */
+int64_t xmr_autophase_workspace_bytes(void);
+int xmr_autophase_search_c64(const void* spec_dev, int n, double u0, double du, int method, int target_idx,
+                             int index_width, int p0_only, double* result_dev, void* workspace_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,185 @@
+"""The fused FID -> phased-spectrum chain on device-resident data (reference semantics, ``mode="single"``).
+
+Two fused passes over the FID batch, no intermediate array in HBM:
+
+  pass 1   K1(statistics only): zero-fill + window + FFT, per-spectrum max |S| / argmax        reads  8*n_in B
+           global first-occurrence argmax (phasing.py:229-231) -> winning spectrum + pivot
+           one-spectrum (p0, p1) search (phasing.py:270-287)
+  pass 2   K1(store + fused phase): same transform, rotated by exp(i*phi_m) on the way out       reads  8*n_in B
+                                                                                                 writes 8*n_out B
+The reference's global-argmax dependency makes the second read of the FID compulsory; the un-phased spectrum is
+never written.  Multi-GPU: each rank runs pass 1 on its shard, the (max, index) pairs are exchanged
+(``xmris_b200.sharding``), the owning rank searches, and (p0, p1, pivot) is broadcast before pass 2.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import device as D
+from .vocab import ATTRS, COORDS, DIMS
+
+
+def chain_geometry(n_in, time_coord, target_points, position, lb):
+    """Host metadata of the chain: padded time axis, window (incl. 1/sqrt(N)), frequency axis, pad_left."""
+    t = np.asarray(time_coord, dtype=np.float64)
+    n_out, pad_left = n_in, 0
+    t_pad = t
+    if target_points is not None and target_points > n_in:
+        n_out = int(target_points)
+        pad = n_out - n_in
+        if position == "end":
+            pad_left = 0
+        elif position == "symmetric":
+            pad_left = pad // 2
+        else:
+            raise ValueError("`position` must be either 'end' or 'symmetric'.")
+        delta = t[1] - t[0]
+        t_pad = (t[0] - pad_left * delta) + np.arange(n_out) * delta   # fid.py:254-263
+    D.check_length(n_out)
+    window = None
+    if lb is not None:
+        window = np.exp(-np.pi * lb * t_pad) / np.sqrt(n_out)           # fid.py:136 with the ortho norm folded in
+    delta = (t_pad[1] - t_pad[0]) if n_out > 1 else 1.0
+    freqs = np.roll(np.fft.fftfreq(n_out, d=delta), n_out // 2)         # fourier.py:95, 31-32
+    return dict(n_out=n_out, pad_left=pad_left, t_pad=t_pad, window=window, freqs=freqs)
+
+
+def phase_turns(freqs, p0, p1, pivot):
+    """Affine phase in turns of the stored bin index m: ``turns(m) = a + b*m`` (phasing.py:56-69, uniform axis)."""
+    x_range = float(freqs.max()) - float(freqs.min())
+    du = (freqs[-1] - freqs[0]) / (len(freqs) - 1) / x_range
+    u0 = (freqs[0] - pivot) / x_range
+    return p0 / 360.0 + (p1 / 360.0) * u0, (p1 / 360.0) * du, u0, du
+
+
+def local_stats(fid_t, geo):
+    """Pass 1 on this rank's shard.  Returns ``(max |S|, flat index)`` of the shard (host scalars)."""
+    _, absmax, argmax = D.fid_to_spectrum(fid_t, n_out=geo["n_out"], pad_left=geo["pad_left"], window=geo["window"],
+                                          store=False, want_stats=True)
+    return D.global_argmax(absmax.reshape(-1), argmax.reshape(-1), geo["n_out"])
+
+
+def search_on_row(fid_row_t, geo, flat_index, method="acme", peak_width=0.5, target_coord=None, p0_only=False,
+                  lb=0.0):
+    """Transform the winning FID alone and run the (p0, p1) search on it.  Returns ``(p0, p1, pivot, fun)``."""
+    from .processing import _index_width, _smooth_slice
+
+    n_out, freqs = geo["n_out"], geo["freqs"]
+    spec, _, _ = D.fid_to_spectrum(fid_row_t.reshape(1, -1), n_out=n_out, pad_left=geo["pad_left"],
+                                   window=geo["window"])
+    work = spec.reshape(n_out)
+    argmax_idx = flat_index % n_out
+    if target_coord is not None:
+        target_idx = int(np.argmin(np.abs(freqs - target_coord)))
+        pivot = float(target_coord)
+    else:
+        target_idx = int(argmax_idx)
+        pivot = float(freqs[target_idx])
+    if lb > 0:
+        work = _smooth_slice(work, freqs, lb)
+    _, _, u0, du = phase_turns(freqs, 0.0, 0.0, pivot)
+    res = D.autophase_search(work.contiguous(), u0, du, method, target_idx, _index_width(freqs, peak_width),
+                             p0_only).cpu().numpy()
+    p0 = float(res[0])
+    p1 = 0.0 if p0_only else float(res[1])
+    return p0, p1, pivot, float(res[2])
+
+
+def apply_pass(fid_t, geo, p0, p1, pivot, out=None):
+    """Pass 2: transform again and rotate by the winning phase on the way out."""
+    a, b, _, _ = phase_turns(geo["freqs"], p0, p1, pivot)
+    spec, _, _ = D.fid_to_spectrum(fid_t, n_out=geo["n_out"], pad_left=geo["pad_left"], window=geo["window"],
+                                   phase_turns=(a, b), out=out)
+    return spec
+
+
+def chain_single(fid_t, time_coord, target_points=None, position="end", lb=None, method="acme", peak_width=0.5,
+                 target_coord=None, p0_only=False, autophase_lb=0.0, out=None, exchange=None):
+    """Full chain with the reference's ``mode="single"`` autophase on a ``[batch, n_in]`` device tensor.
+
+    ``exchange`` (optional) is a callable ``(local_max, local_flat_index, search_fn) -> (p0, p1, pivot, fun)`` used by
+    the multi-GPU path to pick the global winner across ranks; single-GPU callers leave it ``None``.
+    Returns ``(phased spectrum tensor, freqs float64, info dict)``.
+    """
+    n_in = fid_t.shape[-1]
+    flat = fid_t.reshape(-1, n_in)
+    geo = chain_geometry(n_in, time_coord, target_points, position, lb)
+    vmax, findex = local_stats(flat, geo)
+
+    def search():
+        return search_on_row(flat[findex // geo["n_out"]], geo, findex, method, peak_width, target_coord, p0_only,
+                             autophase_lb)
+
+    p0, p1, pivot, fun = search() if exchange is None else exchange(vmax, findex, search)
+    spec = apply_pass(flat, geo, p0, p1, pivot, out=out)
+    spec = spec.reshape(tuple(fid_t.shape[:-1]) + (geo["n_out"],))
+    return spec, geo["freqs"], dict(p0=p0, p1=p1, pivot=pivot, fun=fun, n_out=geo["n_out"], pad_left=geo["pad_left"])
+
+
+def chain_to_spectrum(fid_t, time_coord, target_points=None, position="end", lb=None, out=None):
+    """``zero_fill -> apodize_exp -> to_spectrum`` only (one fused pass)."""
+    n_in = fid_t.shape[-1]
+    geo = chain_geometry(n_in, time_coord, target_points, position, lb)
+    spec, _, _ = D.fid_to_spectrum(fid_t, n_out=geo["n_out"], pad_left=geo["pad_left"], window=geo["window"], out=out)
+    return spec, geo["freqs"], geo
+
+
+def run_chain_dataarray(da, dim, out_dim, target_points, position, lb, autophase_kwargs):
+    """DataArray front end of the fused chain: same coords / attrs / lineage as the chained accessor calls."""
+    from . import processing as P
+    from ._xr import xr
+
+    P._check_dims(da, dim, "process_fid")
+    axis = da.get_axis_num(dim)
+    n_in = da.sizes[dim]
+    t = np.asarray(da.coords[dim].values, dtype=np.float64)
+    fid_t = P._to_device(da.values, axis)
+    attrs = dict(da.attrs)
+    name = da.name
+    padded = target_points is not None and target_points > n_in
+    if padded:
+        attrs[ATTRS.zero_fill_target] = target_points
+        attrs[ATTRS.zero_fill_position] = position
+    if lb is not None:
+        attrs[ATTRS.apodization_lb] = lb
+        if name != dim:
+            name = None
+    target = out_dim if out_dim is not None else dim
+    if autophase_kwargs is None:
+        spec, freqs, _ = chain_to_spectrum(fid_t, t, target_points if padded else None, position, lb)
+        info = None
+    else:
+        kw = dict(autophase_kwargs)
+        mode = kw.pop("mode", "single")
+        if mode == "all":
+            from .pervoxel import chain_all
+
+            spec, freqs, info = chain_all(fid_t, t, target_points if padded else None, position, lb,
+                                          method=kw.get("method", "acme"), peak_width=kw.get("peak_width", 0.5),
+                                          target_coord=kw.get("target_coord"), p0_only=kw.get("p0_only", False))
+        elif mode == "single":
+            spec, freqs, info = chain_single(fid_t, t, target_points if padded else None, position, lb,
+                                             method=kw.get("method", "acme"), peak_width=kw.get("peak_width", 0.5),
+                                             target_coord=kw.get("target_coord"), p0_only=kw.get("p0_only", False),
+                                             autophase_lb=kw.get("lb", 0.0))
+        else:
+            raise ValueError("Mode must be 'single' or 'all'.")
+    dims = tuple(target if d == dim else d for d in da.dims)
+    coords = {k: da.coords[k] for k in da.coords if dim not in da.coords[k].dims}
+    _, var = P._spectrum_coord(dim, out_dim, freqs)
+    coords[target] = var
+    res = xr.DataArray(P._from_device(spec, axis), dims=dims, coords=coords, attrs=attrs, name=name)
+    if info is not None and np.ndim(info["p0"]) == 0:
+        if name != target:
+            res.name = None
+        p1 = info["p1"] if not (autophase_kwargs or {}).get("p0_only", False) else 0.0
+        res.attrs[ATTRS.phase_p0] = np.float64(info["p0"])
+        res.attrs[ATTRS.phase_p1] = np.float64(p1) if p1 != 0.0 or not (autophase_kwargs or {}).get("p0_only") else 0.0
+        res.attrs[ATTRS.phase_pivot] = info["pivot"]
+        res.attrs[ATTRS.phase_pivot_coord] = target
+    elif info is not None:
+        from .pervoxel import attach_per_spectrum_coords
+
+        res = attach_per_spectrum_coords(res, target, info)
+    return res

@@ -1,0 +1,164 @@
+// C ABI: autophase(mode="single") building blocks -- per-row |S| statistics and the one-spectrum (p0, p1) search.
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/xmris_b200.h"
+#include "abi_common.h"
+#include "autophase_search.cuh"
+
+namespace {
+
+using namespace xmr;
+
+// one warp per row: max |S| and its first index (numpy argmax semantics, phasing.py:229-231)
+__global__ void row_absmax_kernel(const float2* __restrict__ spec, long long batch, int n, float* __restrict__ absmax,
+                                  int* __restrict__ argmax) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < batch; row += warps) {
+        const float2* r = spec + row * n;
+        float best = -1.f;
+        int besti = 0x7fffffff;
+        for (int m = lane; m < n; m += 32) {
+            const float2 x = r[m];
+            const float v = x.x * x.x + x.y * x.y;
+            if (v > best) { best = v; besti = m; }
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, off);
+            if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+        }
+        if (lane == 0) { absmax[row] = sqrtf(best); argmax[row] = besti; }
+    }
+}
+
+constexpr int WS_LIST = 4096;   // candidates per ping-pong list
+
+template <int METHOD>
+int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, int p0_only, double* result, Cand* ws,
+               cudaStream_t st) {
+    const int Lc = (n + 31) / 32;
+    int psc = 0;
+    while ((1 << psc) < Lc) ++psc;
+    const size_t smem_coarse = sizeof(float2) * (size_t(n) + (size_t(n) >> psc) + 2);
+    const int per_warp = (n + 7) / 8, Lz = (per_warp + 31) / 32;
+    int psz = 0;
+    while ((1 << psz) < Lz) ++psz;
+    const size_t smem_zoom = sizeof(float2) * (size_t(n) + (size_t(n) >> psz) + 2);
+    cudaError_t e;
+    e = cudaFuncSetAttribute(search_coarse_kernel<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_coarse));
+    if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "cudaFuncSetAttribute(search_coarse)");
+    e = cudaFuncSetAttribute(search_zoom_kernel<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_zoom));
+    if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "cudaFuncSetAttribute(search_zoom)");
+
+    Cand* listA = ws;
+    Cand* listB = ws + WS_LIST;
+
+    SearchParams sp;
+    sp.spec = spec;
+    sp.n = n;
+    sp.u0 = u0;
+    sp.du = du;
+    sp.geom = geom;
+    sp.p0_lo = -180.0;
+    sp.p0_hi = 180.0;
+    sp.p1_lo = p0_only ? 0.0 : -4000.0;
+    sp.p1_hi = p0_only ? 0.0 : 4000.0;
+    sp.p0_step = p0_only ? 0.05 : 2.0;
+    sp.p1_step = 5.0;
+    sp.n_p0 = int((sp.p0_hi - sp.p0_lo) / sp.p0_step + 0.5) + 1;
+    sp.n_p1 = p0_only ? 1 : int((sp.p1_hi - sp.p1_lo) / sp.p1_step + 0.5) + 1;
+    sp.out = listA;
+    const long long items = (long long)sp.n_p1 * ((sp.n_p0 + SEARCH_K - 1) / SEARCH_K);
+    int sms = 148;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long grid = (items + 7) / 8;
+    const long long cap = (long long)sms * 2;
+    if (grid > cap) grid = cap;
+    if (grid > WS_LIST) grid = WS_LIST;
+    search_coarse_kernel<METHOD><<<int(grid), SEARCH_THREADS, smem_coarse, st>>>(sp);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_coarse launch");
+
+    ZoomParams zp;
+    zp.spec = spec;
+    zp.n = n;
+    zp.u0 = u0;
+    zp.du = du;
+    zp.geom = geom;
+    zp.p0_lo = sp.p0_lo;
+    zp.p0_hi = sp.p0_hi;
+    zp.p1_lo = sp.p1_lo;
+    zp.p1_hi = sp.p1_hi;
+    zp.rows = p0_only ? 1 : ZOOM_SIDE;
+    const Cand* prev = listA;
+    int n_prev = int(grid);
+    Cand* cur = listB;
+    double h0 = sp.p0_step, h1 = p0_only ? 0.0 : sp.p1_step;
+    const int levels = 6;
+    for (int lvl = 0; lvl < levels; ++lvl) {
+        zp.prev = prev;
+        zp.n_prev = n_prev;
+        zp.cur = cur;
+        zp.h0 = h0;
+        zp.h1 = h1;
+        const int zgrid = zp.rows * ZOOM_CHUNKS;
+        search_zoom_kernel<METHOD><<<zgrid, SEARCH_THREADS, smem_zoom, st>>>(zp);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_zoom launch");
+        n_prev = zgrid * SEARCH_K;
+        prev = cur;
+        cur = (cur == listB) ? listA : listB;
+        h0 /= 5.0;
+        h1 /= 5.0;
+    }
+    search_finalize_kernel<<<1, SEARCH_THREADS, 0, st>>>(prev, n_prev, result);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_finalize launch");
+    return XMR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int xmr_row_absmax_c64(const void* spec_dev, int64_t batch, int n, float* absmax_dev, int* argmax_dev, void* stream) {
+    if (batch < 0 || n < 1) return xmr_abi::fail(XMR_ERR_BAD_ARG, "bad sizes");
+    if (batch == 0) return XMR_OK;
+    if (!spec_dev || !absmax_dev || !argmax_dev) return xmr_abi::fail(XMR_ERR_BAD_ARG, "NULL pointer");
+    const long long blocks = (batch + 7) / 8;
+    const int grid = int(blocks < 148LL * 8 ? blocks : 148LL * 8);
+    row_absmax_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float2*>(spec_dev), batch, n,
+                                                                         absmax_dev, argmax_dev);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? XMR_OK : xmr_abi::cuda_fail(e, "row_absmax launch");
+}
+
+int64_t xmr_autophase_workspace_bytes(void) { return int64_t(sizeof(Cand)) * 2 * WS_LIST; }
+
+int xmr_autophase_search_c64(const void* spec_dev, int n, double u0, double du, int method, int target_idx,
+                             int index_width, int p0_only, double* result_dev, void* workspace_dev, void* stream) {
+    if (n < 2 || n > 8192) return xmr_abi::fail(XMR_ERR_UNSUPPORTED_N, "autophase search: n=%d must lie in [2, 8192]", n);
+    if (!spec_dev || !result_dev || !workspace_dev) return xmr_abi::fail(XMR_ERR_BAD_ARG, "NULL pointer");
+    if (target_idx < 0 || target_idx >= n || index_width < 1)
+        return xmr_abi::fail(XMR_ERR_BAD_ARG, "bad target_idx=%d / index_width=%d", target_idx, index_width);
+    ScoreGeom g;
+    g.n = n;
+    g.target_idx = target_idx;
+    g.roi_start = target_idx - index_width > 0 ? target_idx - index_width : 0;
+    g.roi_end = target_idx + index_width < n ? target_idx + index_width : n;
+    const float2* s = static_cast<const float2*>(spec_dev);
+    Cand* ws = static_cast<Cand*>(workspace_dev);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (method) {
+        case XMR_METHOD_ACME: return run_search<METHOD_ACME>(s, n, u0, du, g, p0_only, result_dev, ws, st);
+        case XMR_METHOD_PEAK_MINIMA: return run_search<METHOD_PEAK_MINIMA>(s, n, u0, du, g, p0_only, result_dev, ws, st);
+        case XMR_METHOD_POSITIVITY: return run_search<METHOD_POSITIVITY>(s, n, u0, du, g, p0_only, result_dev, ws, st);
+        default: return xmr_abi::fail(XMR_ERR_BAD_ARG, "method=%d", method);
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+// Global (p0, p1) search on ONE spectrum -- the reference's autophase(mode="single") optimisation step
+// (src/xmris/processing/phasing.py:270-287: differential evolution over p0 in [-180,180], p1 in [-4000,4000],
+// polished by L-BFGS-B).  The GPU replaces the stochastic population search by a deterministic dense grid
+// (float32, every SM) followed by nested 21x21 zoom refinements in float64 around the best cell, honouring the
+// same closed box by clamping.  SURVEY.md Appendix C / tests/test_autophase_gpu.py: this lands on the reference's
+// optimum to a few 1e-3 degrees.
+#pragma once
+#include "autophase_eval.cuh"
+
+namespace xmr {
+
+struct Cand {
+    double f, p0, p1, pad;
+};
+
+struct SearchParams {
+    const float2* spec;   // one spectrum, n points (global memory)
+    int n;
+    double u0, du;        // u_m = u0 + du*m = (x_m - pivot)/(x_max - x_min)
+    ScoreGeom geom;
+    double p0_lo, p0_hi, p0_step;
+    int n_p0;
+    double p1_lo, p1_hi, p1_step;
+    int n_p1;
+    Cand* out;
+};
+
+constexpr int SEARCH_K = 8;          // zero-order candidates evaluated per pass over the spectrum
+constexpr int SEARCH_THREADS = 256;
+
+__device__ __forceinline__ int ilog2_ceil(int v) {
+    int s = 0;
+    while ((1 << s) < v) ++s;
+    return s;
+}
+
+// cooperative copy of the spectrum into the padded shared layout idx(m) = m + (m >> padshift)
+__device__ __forceinline__ void load_padded(float2* sp, const float2* __restrict__ g, int n, int padshift) {
+    for (int m = threadIdx.x; m < n; m += blockDim.x) sp[m + (m >> padshift)] = g[m];
+}
+
+
+
+// ---- coarse grid: one warp per (p1, chunk of K p0 values), float32 -----------------------------------------
+template <int METHOD>
+__global__ void __launch_bounds__(SEARCH_THREADS) search_coarse_kernel(const __grid_constant__ SearchParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* sp = reinterpret_cast<float2*>(smem_raw);
+    __shared__ Cand warp_best[SEARCH_THREADS / 32];
+    const int n = p.n;
+    const int L = (n + 31) / 32;
+    const int padshift = ilog2_ceil(L);
+    load_padded(sp, p.spec, n, padshift);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nchunks = (p.n_p0 + SEARCH_K - 1) / SEARCH_K;
+    const long long items = (long long)p.n_p1 * nchunks;
+    const int m0 = min(lane << padshift, n), m1 = min((lane + 1) << padshift, n);
+
+    double best_f = CUDART_INF, best_p0 = p.p0_lo, best_p1 = p.p1_lo;
+    for (long long item = (long long)blockIdx.x * (SEARCH_THREADS / 32) + warp; item < items;
+         item += (long long)gridDim.x * (SEARCH_THREADS / 32)) {
+        const int i1 = int(item / nchunks), ch = int(item - (long long)i1 * nchunks);
+        const double p1 = fmin(p.p1_lo + i1 * p.p1_step, p.p1_hi);
+        float c0[SEARCH_K], s0[SEARCH_K];
+        double p0k[SEARCH_K];
+#pragma unroll
+        for (int k = 0; k < SEARCH_K; ++k) {
+            p0k[k] = fmin(p.p0_lo + (ch * SEARCH_K + k) * p.p0_step, p.p0_hi);
+            sincospif(float(p0k[k] / 180.0), &s0[k], &c0[k]);
+        }
+        Acc<float, METHOD, SEARCH_K> acc;
+        acc.init();
+        lane_accumulate_rt<float, METHOD, SEARCH_K>(sp, padshift, m0, m1, p.geom, float(p1 / 360.0), float(p.u0),
+                                                    float(p.du), c0, s0, acc);
+        acc.warp_reduce();
+#pragma unroll
+        for (int k = 0; k < SEARCH_K; ++k) {
+            const float f = acc.score(k, p.geom);
+            if (double(f) < best_f) { best_f = double(f); best_p0 = p0k[k]; best_p1 = p1; }
+        }
+    }
+    if (lane == 0) { warp_best[warp].f = best_f; warp_best[warp].p0 = best_p0; warp_best[warp].p1 = best_p1; warp_best[warp].pad = 0; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Cand b = warp_best[0];
+        for (int w = 1; w < SEARCH_THREADS / 32; ++w)
+            if (warp_best[w].f < b.f) b = warp_best[w];
+        p.out[blockIdx.x] = b;
+    }
+}
+
+struct ZoomParams {
+    const float2* spec;
+    int n;
+    double u0, du;
+    ScoreGeom geom;
+    const Cand* prev;   // candidates of the previous level (or the per-CTA bests of the coarse grid)
+    int n_prev;
+    double h0, h1;      // half-widths of this level's window around the best previous candidate
+    double p0_lo, p0_hi, p1_lo, p1_hi;
+    int rows;           // 21 (two parameters) or 1 (p0 only)
+    Cand* cur;          // rows * 3 * SEARCH_K candidates
+};
+
+constexpr int ZOOM_SIDE = 21;   // 21 x 21 points per level, spacing h/10
+constexpr int ZOOM_CHUNKS = 3;  // 3 * SEARCH_K = 24 >= 21
+
+// block-wide argmin of a candidate list (lowest index wins ties) -> broadcast
+__device__ __forceinline__ Cand block_argmin(const Cand* list, int n_list) {
+    __shared__ double sf[SEARCH_THREADS / 32];
+    __shared__ int si[SEARCH_THREADS / 32];
+    __shared__ int s_best;
+    double f = CUDART_INF;
+    int idx = 0x7fffffff;
+    for (int i = threadIdx.x; i < n_list; i += blockDim.x) {
+        const double v = list[i].f;
+        if (v < f || (v == f && i < idx)) { f = v; idx = i; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double of = __shfl_xor_sync(0xffffffffu, f, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+        if (of < f || (of == f && oi < idx)) { f = of; idx = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sf[threadIdx.x >> 5] = f; si[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < int(blockDim.x >> 5); ++w)
+            if (sf[w] < f || (sf[w] == f && si[w] < idx)) { f = sf[w]; idx = si[w]; }
+        s_best = (idx == 0x7fffffff) ? 0 : idx;
+    }
+    __syncthreads();
+    return list[s_best];
+}
+
+// ---- zoom level: one CTA per (p1 row, chunk of K p0 values), float64, the 8 warps split the spectrum ---------
+template <int METHOD>
+__global__ void __launch_bounds__(SEARCH_THREADS) search_zoom_kernel(const __grid_constant__ ZoomParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* sp = reinterpret_cast<float2*>(smem_raw);
+    __shared__ double part[SEARCH_THREADS / 32][SEARCH_K][4];
+    const int n = p.n;
+    constexpr int NW = SEARCH_THREADS / 32;
+    const int per_warp = (n + NW - 1) / NW;
+    const int L = (per_warp + 31) / 32;
+    const int padshift = ilog2_ceil(L);
+    load_padded(sp, p.spec, n, padshift);
+    const Cand centre = block_argmin(p.prev, p.n_prev);   // contains the barriers that also publish `sp`
+
+    const int row = blockIdx.x / ZOOM_CHUNKS, ch = blockIdx.x % ZOOM_CHUNKS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double p1 = (p.rows == 1) ? centre.p1
+                                    : fmin(fmax(centre.p1 + (row - ZOOM_SIDE / 2) * (p.h1 / (ZOOM_SIDE / 2)), p.p1_lo), p.p1_hi);
+    double c0[SEARCH_K], s0[SEARCH_K], p0k[SEARCH_K];
+#pragma unroll
+    for (int k = 0; k < SEARCH_K; ++k) {
+        const int i = min(ch * SEARCH_K + k, ZOOM_SIDE - 1);
+        p0k[k] = fmin(fmax(centre.p0 + (i - ZOOM_SIDE / 2) * (p.h0 / (ZOOM_SIDE / 2)), p.p0_lo), p.p0_hi);
+        sincospi(p0k[k] / 180.0, &s0[k], &c0[k]);
+    }
+    const int w0 = min(warp * per_warp, n), w1 = min(w0 + per_warp, n);
+    const int m0 = min(w0 + (lane << padshift), w1), m1 = min(m0 + (1 << padshift), w1);
+    Acc<double, METHOD, SEARCH_K> acc;
+    acc.init();
+    lane_accumulate_rt<double, METHOD, SEARCH_K>(sp, padshift, m0, m1, p.geom, p1 / 360.0, p.u0, p.du, c0, s0, acc);
+    acc.warp_reduce();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < SEARCH_K; ++k)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) part[warp][k][s] = acc.a[k][s];
+    }
+    __syncthreads();
+    if (threadIdx.x < SEARCH_K) {
+        const int k = threadIdx.x;
+        Acc<double, METHOD, 1> tot;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            double v = part[0][k][s];
+            for (int w = 1; w < NW; ++w) v = Acc<double, METHOD, 1>::comb(s, v, part[w][k][s]);
+            tot.a[0][s] = v;
+        }
+        Cand c;
+        c.f = tot.score(0, p.geom);
+        if (!(c.f == c.f)) c.f = CUDART_INF;   // NaN never wins
+        // select p0k[k] without dynamic register indexing
+        double myp0 = p0k[0];
+#pragma unroll
+        for (int kk = 1; kk < SEARCH_K; ++kk)
+            if (kk == k) myp0 = p0k[kk];
+        c.p0 = myp0;
+        c.p1 = p1;
+        c.pad = 0;
+        p.cur[blockIdx.x * SEARCH_K + k] = c;
+    }
+}
+
+// final pick: result = {p0, p1, f, 0}
+__global__ void search_finalize_kernel(const Cand* list, int n_list, double* result) {
+    const Cand b = block_argmin(list, n_list);
+    if (threadIdx.x == 0) {
+        result[0] = b.p0;
+        result[1] = b.p1;
+        result[2] = b.f;
+        result[3] = 0.0;
+    }
+}
+
+}  // namespace xmr

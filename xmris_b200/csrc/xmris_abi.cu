@@ -9,12 +9,11 @@
 #include <vector>
 
 #include "../../include/xmris_b200.h"
+#include "abi_common.h"
 #include "k1_launch.cuh"
 
-namespace {
-
+namespace xmr_abi {
 thread_local char g_err[512] = "";
-
 int fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -25,6 +24,11 @@ int fail(int code, const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
     return fail(XMR_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
+}  // namespace xmr_abi
+
+namespace {
+using xmr_abi::cuda_fail;
+using xmr_abi::fail;
 
 bool supported_n(int n) { return n >= 16 && n <= 8192 && (n & (n - 1)) == 0; }
 
@@ -145,7 +149,7 @@ int grid_for(long long total, int block) {
 extern "C" {
 
 int xmr_version(void) { return 100; }
-const char* xmr_last_error(void) { return g_err; }
+const char* xmr_last_error(void) { return xmr_abi::g_err; }
 
 int xmr_fid_to_spectrum_c64(const void* fid_dev, void* spec_dev, int64_t batch, int n_in, int n_out, int pad_left,
                             int window_mode, const float* window_dev, const float* win_rows_host, float scale,

@@ -215,3 +215,53 @@ def global_argmax(absmax, argmax, n, stream=None):
                                          _stream_ptr(stream)))
     host = out.cpu().numpy()
     return float(host[:4].view(np.float32)[0]), int(host[8:16].view(np.int64)[0])
+
+
+def row_absmax(spec, stream=None):
+    """Per-spectrum ``max |S|`` (float32) and its first index (int32) along the last axis."""
+    torch = _torch()
+    lib = _lib.load()
+    _require_cuda(spec, "spec")
+    n = spec.shape[-1]
+    bshape = tuple(spec.shape[:-1])
+    absmax = torch.empty(bshape, dtype=torch.float32, device=spec.device)
+    argmax = torch.empty(bshape, dtype=torch.int32, device=spec.device)
+    with torch.cuda.device(spec.device):
+        _lib.check(lib.xmr_row_absmax_c64(_ptr(spec), spec.numel() // max(n, 1), n, _ptr(absmax), _ptr(argmax),
+                                          _stream_ptr(stream)))
+    return absmax, argmax
+
+
+_workspaces = {}
+
+
+def _workspace(device):
+    torch = _torch()
+    key = (device.type, device.index)
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.empty(int(_lib.load().xmr_autophase_workspace_bytes()), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def autophase_search(spec1d, u0, du, method="acme", target_idx=0, index_width=1, p0_only=False, stream=None):
+    """Global (p0, p1) search on one device-resident spectrum.  Returns a CUDA float64 tensor ``[p0, p1, fun, 0]``.
+
+    ``u_m = u0 + du*m`` is the reference's normalised phase ramp ``(x_m - pivot)/(x_max - x_min)``.
+    """
+    torch = _torch()
+    lib = _lib.load()
+    _require_cuda(spec1d, "spec1d")
+    if spec1d.dim() != 1:
+        raise ValueError("autophase_search works on one 1-D spectrum")
+    if method not in _lib.METHODS:
+        raise ValueError("Method must be 'acme', 'peak_minima', or 'positivity'")
+    n = spec1d.shape[0]
+    result = torch.empty(4, dtype=torch.float64, device=spec1d.device)
+    ws = _workspace(spec1d.device)
+    with torch.cuda.device(spec1d.device):
+        _lib.check(lib.xmr_autophase_search_c64(_ptr(spec1d), n, float(u0), float(du), _lib.METHODS[method],
+                                                int(target_idx), int(index_width), int(bool(p0_only)), _ptr(result),
+                                                _ptr(ws), _stream_ptr(stream)))
+    return result
