@@ -53,10 +53,21 @@ def phase_turns(freqs, p0, p1, pivot):
     return p0 / 360.0 + (p1 / 360.0) * u0, (p1 / 360.0) * du, u0, du
 
 
+def _win(geo, device):
+    """The chain's window, uploaded once per (geometry, device)."""
+    if geo["window"] is None:
+        return None
+    cache = geo.setdefault("_prepared", {})
+    key = (device.type, device.index)
+    if key not in cache:
+        cache[key] = D.PreparedWindow(geo["window"], geo["n_out"], device)
+    return cache[key]
+
+
 def local_stats(fid_t, geo):
     """Pass 1 on this rank's shard.  Returns ``(max |S|, flat index)`` of the shard (host scalars)."""
-    _, absmax, argmax = D.fid_to_spectrum(fid_t, n_out=geo["n_out"], pad_left=geo["pad_left"], window=geo["window"],
-                                          store=False, want_stats=True)
+    _, absmax, argmax = D.fid_to_spectrum(fid_t, n_out=geo["n_out"], pad_left=geo["pad_left"],
+                                          window=_win(geo, fid_t.device), store=False, want_stats=True)
     return D.global_argmax(absmax.reshape(-1), argmax.reshape(-1), geo["n_out"])
 
 
@@ -67,7 +78,7 @@ def search_on_row(fid_row_t, geo, flat_index, method="acme", peak_width=0.5, tar
 
     n_out, freqs = geo["n_out"], geo["freqs"]
     spec, _, _ = D.fid_to_spectrum(fid_row_t.reshape(1, -1), n_out=n_out, pad_left=geo["pad_left"],
-                                   window=geo["window"])
+                                   window=_win(geo, fid_row_t.device))
     work = spec.reshape(n_out)
     argmax_idx = flat_index % n_out
     if target_coord is not None:
@@ -89,8 +100,8 @@ def search_on_row(fid_row_t, geo, flat_index, method="acme", peak_width=0.5, tar
 def apply_pass(fid_t, geo, p0, p1, pivot, out=None):
     """Pass 2: transform again and rotate by the winning phase on the way out."""
     a, b, _, _ = phase_turns(geo["freqs"], p0, p1, pivot)
-    spec, _, _ = D.fid_to_spectrum(fid_t, n_out=geo["n_out"], pad_left=geo["pad_left"], window=geo["window"],
-                                   phase_turns=(a, b), out=out)
+    spec, _, _ = D.fid_to_spectrum(fid_t, n_out=geo["n_out"], pad_left=geo["pad_left"],
+                                   window=_win(geo, fid_t.device), phase_turns=(a, b), out=out)
     return spec
 
 
@@ -121,7 +132,8 @@ def chain_to_spectrum(fid_t, time_coord, target_points=None, position="end", lb=
     """``zero_fill -> apodize_exp -> to_spectrum`` only (one fused pass)."""
     n_in = fid_t.shape[-1]
     geo = chain_geometry(n_in, time_coord, target_points, position, lb)
-    spec, _, _ = D.fid_to_spectrum(fid_t, n_out=geo["n_out"], pad_left=geo["pad_left"], window=geo["window"], out=out)
+    spec, _, _ = D.fid_to_spectrum(fid_t, n_out=geo["n_out"], pad_left=geo["pad_left"],
+                                   window=_win(geo, fid_t.device), out=out)
     return spec, geo["freqs"], geo
 
 

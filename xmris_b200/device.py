@@ -79,6 +79,18 @@ def split_window(w: np.ndarray, n_out: int):
     return _lib.WIN_TABLE, w.astype(np.float32), None
 
 
+class PreparedWindow:
+    """A window already factored and uploaded to one device (avoids a small H2D copy per launch)."""
+
+    def __init__(self, window, n_out, device):
+        torch = _torch()
+        self.n_out = n_out
+        self.mode, table, rows = split_window(window, n_out)
+        self.dev = torch.from_numpy(np.ascontiguousarray(table)).to(device)
+        self.rows = rows
+        self.device = device
+
+
 # ---------------------------------------------------------------------------------------------------------
 # K1: fused FID -> spectrum
 # ---------------------------------------------------------------------------------------------------------
@@ -90,7 +102,7 @@ def fid_to_spectrum(fid, n_out=None, pad_left=0, window=None, scale=None, invers
 
     fid          complex64 CUDA tensor ``[..., n_in]``
     n_out        transform length (>= n_in); zero filling is implicit
-    window       float64 numpy ``[n_out]`` multiplied before the transform (should include ``1/sqrt(n_out)`` for the
+    window       float64 numpy ``[n_out]`` (or a :class:`PreparedWindow`) multiplied before the transform (should include ``1/sqrt(n_out)`` for the
                  reference's ortho norm); ``None`` -> multiply by ``scale`` (default ``1/sqrt(n_out)``)
     out_shift    index rotation of the stored bins; default ``n_out//2`` (= fftshift, ``fourier.py:31-32``)
     phase_turns  ``(a, b)``: multiply stored bin m by ``exp(2 pi i (a + b m))``
@@ -123,7 +135,11 @@ def fid_to_spectrum(fid, n_out=None, pad_left=0, window=None, scale=None, invers
         absmax = torch.empty(batch_shape, dtype=torch.float32, device=dev)
         argmax = torch.empty(batch_shape, dtype=torch.int32, device=dev)
     win_mode, win_dev, rows = _lib.WIN_NONE, None, None
-    if window is not None:
+    if isinstance(window, PreparedWindow):
+        if window.n_out != n_out or window.device != dev:
+            raise ValueError("PreparedWindow was built for another length / device")
+        win_mode, win_dev, rows = window.mode, window.dev, window.rows
+    elif window is not None:
         win_mode, table, rows = split_window(window, n_out)
         win_dev = torch.from_numpy(np.ascontiguousarray(table)).to(dev)
     rows_arr = (ctypes.c_float * 32)(*([1.0] * 32))
