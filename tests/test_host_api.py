@@ -1,0 +1,180 @@
+"""CPU: host-side logic of the drop-in layer -- signatures/defaults, error text, metadata helpers, the xarray stand-in,
+window factoring, phase-ramp arithmetic, shard bookkeeping and the 2-rank exchange over gloo."""
+
+import inspect
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import xmris_b200
+from xmris_b200 import chain, device, processing, sharding
+from xmris_b200.accessor import XmrisB200Accessor
+from xmris_b200.vocab import ATTRS, COORDS, DIMS
+from oracle import xmris_oracle as orc
+
+xr = xmris_b200.xr
+
+
+def _defaults(fn):
+    return {k: v.default for k, v in inspect.signature(fn).parameters.items() if v.default is not inspect.Parameter.empty}
+
+
+def test_accessor_defaults_match_reference():
+    # reference tests/test_core.py:509-552 + accessor.py:452, 490, 526-531, 599-605, 630-638
+    A = XmrisB200Accessor
+    assert _defaults(A.apodize_exp) == {"dim": "time", "lb": 1.0}
+    assert _defaults(A.to_spectrum) == {"dim": "time", "out_dim": "frequency"}
+    assert _defaults(A.zero_fill) == {"dim": "time", "target_points": 1024, "position": "end"}
+    assert _defaults(A.phase) == {"dim": "frequency", "p0": 0.0, "p1": 0.0, "pivot": None}
+    assert _defaults(A.autophase) == {"dim": "frequency", "method": "acme", "peak_width": 100, "lb": 0.0,
+                                      "temp_time_dim": "time"}
+    assert _defaults(processing.autophase) == {"dim": "frequency", "method": "acme", "mode": "single", "peak_width": 0.5,
+                                               "target_coord": None, "p0_only": False, "lb": 0.0, "temp_time_dim": "time"}
+    assert DIMS.time == "time" and DIMS.frequency == "frequency" and COORDS.frequency.unit == "Hz"
+    assert COORDS.chemical_shift.long_name == "Chemical Shift" and ATTRS.phase_pivot_coord == "phase_pivot_coord"
+
+
+def test_check_dims_error_text():
+    # reference tests/test_core.py:411-440
+    da = xr.DataArray(np.zeros((2, 4)), dims=["voxel", "t"])
+    with pytest.raises(ValueError) as e:
+        processing._check_dims(da, "time", "apodize_exp")
+    msg = str(e.value)
+    assert "missing dimension" in msg and "['voxel', 't']" in msg and "apodize_exp" in msg
+    assert "obj.rename({'time': 'correct_name'})" in msg
+    processing._check_dims(da, ["voxel", "t"], "fft")
+    for fn in (xmris_b200.zero_fill, xmris_b200.apodize_exp, xmris_b200.to_spectrum, xmris_b200.phase, xmris_b200.autophase):
+        with pytest.raises(ValueError, match="missing dimension"):
+            fn(da, dim="nope")
+
+
+def test_accessor_registered_and_no_cpu_fallback():
+    import torch
+
+    da = xr.DataArray(np.zeros((2, 16), complex), dims=["v", "time"], coords={"time": np.arange(16.0)})
+    assert isinstance(da.xmr, XmrisB200Accessor) and da.xmr is da.xmr
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            da.xmr.to_spectrum()
+        with pytest.raises(TypeError, match="CUDA"):
+            device.fid_to_spectrum(torch.zeros((2, 16), dtype=torch.complex64))
+    same = da.xmr.zero_fill(target_points=8)       # no-op path never touches the device (fid.py:234-236)
+    assert same.attrs == {} and same.shape == (2, 16)
+    with pytest.raises(ValueError, match="Mode"):
+        da.xmr.autophase(dim="time", mode="nope")
+    with pytest.raises(ValueError, match="Method"):
+        da.xmr.autophase(dim="time", method="nope")
+
+
+def test_xarray_lite_semantics():
+    t = np.arange(4.0)
+    da = xr.DataArray(np.arange(8.0).reshape(2, 4), dims=["v", "time"], coords={"time": ("time", t, {"units": "s"})},
+                      attrs={"a": 1}, name="x")
+    w = np.exp(-da.coords["time"])
+    prod = (da * w).transpose(*da.dims)
+    assert prod.attrs == {} and prod.name is None and prod.dims == ("v", "time")     # attrs dropped, names differ
+    np.testing.assert_allclose(prod.values, da.values * np.exp(-t))
+    p = da.pad({"time": (1, 2)}, mode="constant", constant_values=0)
+    assert p.shape == (2, 7) and np.isnan(p.coords["time"].values[[0, 5, 6]]).all() and p.attrs == {"a": 1}
+    r = da.roll({"time": 2}, roll_coords=True)
+    np.testing.assert_array_equal(r.coords["time"].values, np.roll(t, 2))
+    s = da.isel({"v": 1})
+    assert s.dims == ("time",) and s.shape == (4,)
+    rn = da.rename({"time": "frequency"})
+    assert rn.dims == ("v", "frequency") and "frequency" in rn.coords and "time" not in rn.coords
+    c = da.copy(data=np.zeros((2, 4)))
+    assert c.attrs == {"a": 1} and c.name == "x" and c.coords["time"].attrs == {"units": "s"}
+    assert float(da.coords["time"].max()) == 3.0 and da.get_axis_num("time") == 1
+    with pytest.raises(KeyError):
+        xr.DataArray(np.zeros(3), dims=["q"]).coords["q"]
+
+
+def test_split_window_and_geometry():
+    t = 1e-3 + np.arange(4096) / 5000.0
+    w = np.exp(-np.pi * 5.0 * t) / 64.0
+    mode, cols, rows = device.split_window(w, 4096)
+    assert mode == device._lib.WIN_SEPARABLE and cols.shape == (256,) and rows.shape == (16,)
+    recon = (rows[:, None].astype(np.float64) * cols[None, :]).ravel()
+    np.testing.assert_allclose(recon, w, rtol=3e-7)
+    mode, table, rows = device.split_window(np.linspace(1, 2, 4096), 4096)
+    assert mode == device._lib.WIN_TABLE and rows is None and table.shape == (4096,)
+    mode, table, rows = device.split_window(np.linspace(1, 2, 128), 128)
+    assert mode == device._lib.WIN_SEPARABLE and table.shape == (128,)
+    with pytest.raises(ValueError, match="not supported"):
+        device.check_length(1972)
+    geo = chain.chain_geometry(1024, np.linspace(0, 1, 1024), 2048, "end", 5.0)
+    _, t_ref, _ = orc.zero_fill(np.zeros(1024), 0, np.linspace(0, 1, 1024), 2048, "end")
+    np.testing.assert_array_equal(geo["t_pad"], t_ref)
+    ref_spec, ref_freq = orc.to_spectrum(np.zeros(2048, complex), 0, t_ref)
+    np.testing.assert_array_equal(geo["freqs"], ref_freq)
+    geo = chain.chain_geometry(32, np.arange(32.0) - 16, 129 - 1, "symmetric", None)
+    assert geo["pad_left"] == 48 and geo["window"] is None
+    with pytest.raises(ValueError, match="position"):
+        chain.chain_geometry(32, np.arange(32.0), 64, "middle", None)
+
+
+def test_phase_turns_equal_reference_ramp():
+    freqs = np.roll(np.fft.fftfreq(2048, d=1 / 5000.0), 1024)
+    for p0, p1, pivot in [(33.0, -725.0, freqs[700]), (-180.0, 4000.0, 123.4), (12.0, 0.0, freqs[0])]:
+        a, b, u0, du = chain.phase_turns(freqs, p0, p1, pivot)
+        ref = orc.phase_array(freqs, p0, p1, pivot) / (2 * np.pi)
+        np.testing.assert_allclose(a + b * np.arange(2048), ref, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(u0 + du * np.arange(2048), (freqs - pivot) / (freqs.max() - freqs.min()), atol=1e-14)
+    desc = freqs[::-1].copy()      # descending axis (ppm-like): the ramp keeps the reference's sign convention
+    u0, du = processing._affine_ramp(desc, desc[10])
+    np.testing.assert_allclose(u0 + du * np.arange(2048), (desc - desc[10]) / (desc.max() - desc.min()), atol=1e-14)
+    with pytest.raises(ValueError, match="uniform"):
+        processing._affine_ramp(np.cumsum(np.linspace(1, 2, 64)), 3.0)
+
+
+def test_shard_bounds_and_winner():
+    for n, w in [(10, 3), (1 << 20, 8), (5, 8), (0, 2)]:
+        spans = [sharding.shard_bounds(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+    assert sharding.pick_winner([1.0, 7.0, 7.0], [5, 6, 7], [0, 100, 200]) == (1, 106)   # tie -> lowest rank
+    assert sharding.pick_winner([-np.inf, 2.0], [0, 3], [0, 40]) == (1, 43)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = torch.device("cpu")
+    n_out, rows = 64, 10
+    exch = sharding.make_exchange(dist, dev, n_out, rank * rows * n_out)
+    called = []
+
+    def search():
+        called.append(rank)
+        return 1.5 + rank, 2.5, 3.5, 4.5
+
+    local_max, local_flat = [(3.0, 17), (9.0, 130)][rank]
+    res = exch(local_max, local_flat, search)
+    q.put((rank, res, called))
+    dist.destroy_process_group()
+
+
+def test_two_rank_exchange_gloo():
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    # rank 1 holds the global maximum: only it searches, both ranks receive its answer
+    assert got[0][1] == got[1][1] == (2.5, 2.5, 3.5, 4.5)
+    assert got[0][2] == [] and got[1][2] == [1]
