@@ -101,6 +101,21 @@ int64_t xmr_autophase_workspace_bytes(void);
 int xmr_autophase_search_c64(const void* spec_dev, int n, double u0, double du, int method, int target_idx,
                              int index_width, int p0_only, double* result_dev, void* workspace_dev, void* stream);
 
+/* The whole chain per voxel in ONE pass (autophase mode="all"; the reference's NotImplementedError branch,
+ * phasing.py:219-222, defined as "the reference's autophase applied to every 1-D spectrum on its own"):
+ *   zero_fill -> apodize -> FFT -> fftshift -> per-spectrum (p0, p1) search on the shared-memory resident
+ *   spectrum (pivot = that spectrum's own |S| maximum, phasing.py:229-238) -> phase -> store.
+ *   in_dev            [batch, n_in] FIDs, or (input_is_spectrum=1, n_in == n_out) spectra in stored order
+ *   du                u_m = u0 + du*m; u0 = -du*argmax per voxel, or u0_fixed when fixed_pivot=1 (target_coord)
+ *   p0_dev, p1_dev    double[batch] degrees; pivot_dev int[batch] (index of the maximum); fun_dev float[batch]
+ * n_out must be a power of two in [512, 8192].
+ */
+int xmr_chain_each_c64(const void* in_dev, void* out_dev, int64_t batch, int n_in, int n_out, int pad_left,
+                       int input_is_spectrum, int window_mode, const float* window_dev, const float* win_rows_host,
+                       float scale, int method, double du, int fixed_pivot, double u0_fixed, int fixed_target,
+                       int index_width, int p0_only, double* p0_dev, double* p1_dev, int* pivot_dev, float* fun_dev,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,14 @@ enum : int { METHOD_ACME = 0, METHOD_PEAK_MINIMA = 1, METHOD_POSITIVITY = 2 };
 template <typename R> struct RealOps;
 template <> struct RealOps<float> {
     static __device__ __forceinline__ void sincospi2(float turns, float* s, float* c) { sincospif(2.0f * turns, s, c); }
-    static __device__ __forceinline__ float log2r(float x) { return __log2f(x); }
+    static __device__ __forceinline__ float log2r(float x) {   // one MUFU.LG2, denormals flushed (x >= tiny() here)
+        float y;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+        return y;
+    }
+    static __device__ __forceinline__ float mn(float a, float b) { return fminf(a, b); }
+    static __device__ __forceinline__ float mx(float a, float b) { return fmaxf(a, b); }
+    static __device__ __forceinline__ float ab(float a) { return fabsf(a); }
     static __device__ __forceinline__ float tiny() { return 1.17549435e-38f; }
     static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
     static __device__ __forceinline__ float lnr(float x) { return logf(x); }
@@ -32,6 +39,9 @@ template <> struct RealOps<float> {
 template <> struct RealOps<double> {
     static __device__ __forceinline__ void sincospi2(double turns, double* s, double* c) { sincospi(2.0 * turns, s, c); }
     static __device__ __forceinline__ double log2r(double x) { return log2(x); }
+    static __device__ __forceinline__ double mn(double a, double b) { return fmin(a, b); }
+    static __device__ __forceinline__ double mx(double a, double b) { return fmax(a, b); }
+    static __device__ __forceinline__ double ab(double a) { return fabs(a); }
     static __device__ __forceinline__ double tiny() { return 2.2250738585072014e-308; }
     static __device__ __forceinline__ double inf() { return CUDART_INF; }
     static __device__ __forceinline__ double lnr(double x) { return log(x); }
@@ -113,42 +123,76 @@ __device__ __forceinline__ void lane_accumulate_rt(const float2* sp, int padshif
         ti -= floor(ti);
         RealOps<R>::sincospi2(ti, &si, &ci);
     }
-    R dprev[K];
-    const int last = (METHOD == METHOD_ACME) ? (m1 < g.n ? m1 : g.n - 1) : (m1 - 1);
-    for (int m = m0; m <= last; ++m) {
+    using O = RealOps<R>;
+    if constexpr (METHOD == METHOD_ACME) {
+        // point m0: no difference yet.  points m0+1 .. m1-1: full body.  point m1 (if it exists): closes the last
+        // difference only (it belongs to the next lane).  No predicates inside the hot loop.
+        R dprev[K];
+        {
+            const float2 S = sp[m0 + (m0 >> padshift)];
+            const R wx = R(S.x) * cr - R(S.y) * sr, wy = R(S.x) * sr + R(S.y) * cr;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const R d = wx * c0[k] - wy * s0[k];
+                dprev[k] = d;
+                const R neg = O::mn(d, R(0));
+                acc.a[k][2] += neg * neg;
+                acc.a[k][3] = O::mx(acc.a[k][3], d);
+            }
+            const R ncr = cr * ci - sr * si;
+            sr = cr * si + sr * ci;
+            cr = ncr;
+        }
+#pragma unroll 2
+        for (int m = m0 + 1; m < m1; ++m) {
+            const float2 S = sp[m + (m >> padshift)];
+            const R wx = R(S.x) * cr - R(S.y) * sr, wy = R(S.x) * sr + R(S.y) * cr;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const R d = wx * c0[k] - wy * s0[k];
+                const R D = O::ab(d - dprev[k]);
+                dprev[k] = d;
+                acc.a[k][0] += D;
+                acc.a[k][1] += D * O::log2r(O::mx(D, O::tiny()));
+                const R neg = O::mn(d, R(0));
+                acc.a[k][2] += neg * neg;
+                acc.a[k][3] = O::mx(acc.a[k][3], d);
+            }
+            const R ncr = cr * ci - sr * si;
+            sr = cr * si + sr * ci;
+            cr = ncr;
+        }
+        if (m1 < g.n) {
+            const float2 S = sp[m1 + (m1 >> padshift)];
+            const R wx = R(S.x) * cr - R(S.y) * sr, wy = R(S.x) * sr + R(S.y) * cr;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const R D = O::ab((wx * c0[k] - wy * s0[k]) - dprev[k]);
+                acc.a[k][0] += D;
+                acc.a[k][1] += D * O::log2r(O::mx(D, O::tiny()));
+            }
+        }
+    } else {
+    for (int m = m0; m < m1; ++m) {
         const float2 S = sp[m + (m >> padshift)];
         const R wx = R(S.x) * cr - R(S.y) * sr;
         const R wy = R(S.x) * sr + R(S.y) * cr;
-        const bool own = (m < m1);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const R d = wx * c0[k] - wy * s0[k];
-            if (METHOD == METHOD_ACME) {
-                if (m > m0) {
-                    R D = d - dprev[k];
-                    D = D < 0 ? -D : D;
-                    acc.a[k][0] += D;
-                    const R Dl = D > RealOps<R>::tiny() ? D : RealOps<R>::tiny();
-                    acc.a[k][1] += D * RealOps<R>::log2r(Dl);
-                }
-                dprev[k] = d;
-                if (own) {
-                    const R neg = d < 0 ? d : R(0);
-                    acc.a[k][2] += neg * neg;
-                    acc.a[k][3] = acc.a[k][3] > d ? acc.a[k][3] : d;
-                }
-            } else if (METHOD == METHOD_POSITIVITY) {
-                acc.a[k][0] += d < 0 ? -d : R(0);
-                acc.a[k][1] += d > 0 ? d : R(0);
+            if (METHOD == METHOD_POSITIVITY) {
+                acc.a[k][0] -= O::mn(d, R(0));
+                acc.a[k][1] += O::mx(d, R(0));
             } else {
-                if (m < g.target_idx) acc.a[k][0] = acc.a[k][0] < d ? acc.a[k][0] : d;
-                else acc.a[k][1] = acc.a[k][1] < d ? acc.a[k][1] : d;
+                if (m < g.target_idx) acc.a[k][0] = O::mn(acc.a[k][0], d);
+                else acc.a[k][1] = O::mn(acc.a[k][1], d);
                 if (m == g.target_idx) acc.a[k][2] = d;
             }
         }
         const R ncr = cr * ci - sr * si;
         sr = cr * si + sr * ci;
         cr = ncr;
+    }
     }
 }
 

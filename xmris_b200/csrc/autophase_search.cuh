@@ -157,7 +157,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_zoom_kernel(const __gri
 #pragma unroll
     for (int k = 0; k < SEARCH_K; ++k) {
         const int i = min(ch * SEARCH_K + k, ZOOM_SIDE - 1);
-        p0k[k] = fmin(fmax(centre.p0 + (i - ZOOM_SIDE / 2) * (p.h0 / (ZOOM_SIDE / 2)), p.p0_lo), p.p0_hi);
+        // p0 is periodic: a window that leaves the closed box [-180, 180] re-enters on the other side
+        double q0 = centre.p0 + (i - ZOOM_SIDE / 2) * (p.h0 / (ZOOM_SIDE / 2));
+        q0 = q0 > p.p0_hi ? q0 - 360.0 : (q0 < p.p0_lo ? q0 + 360.0 : q0);
+        p0k[k] = q0;
         sincospi(p0k[k] / 180.0, &s0[k], &c0[k]);
     }
     const int w0 = min(warp * per_warp, n), w1 = min(w0 + per_warp, n);

@@ -33,6 +33,9 @@ using xmr_abi::fail;
 bool supported_n(int n) { return n >= 16 && n <= 8192 && (n & (n - 1)) == 0; }
 
 // ---- per-(device, N) twiddle tables: exp(-2 pi i k / N) rounded from float64 -----------------------------
+}  // namespace
+
+namespace xmr_abi {
 std::mutex g_tw_mutex;
 std::map<std::pair<int, int>, float2*> g_tw;
 
@@ -65,6 +68,10 @@ int get_twiddles(int n, const float2** out) {
     *out = d;
     return XMR_OK;
 }
+}  // namespace xmr_abi
+
+namespace {
+using xmr_abi::get_twiddles;
 
 // ---- elementwise kernels --------------------------------------------------------------------------------
 __global__ void zero_fill_kernel(const float2* __restrict__ in, float2* __restrict__ out, long long batch, int n_in,
