@@ -58,7 +58,8 @@ const char* xmr_last_error(void);
  *   pad_left  zeros before the data ("symmetric" position: (n_out-n_in)/2; "end": 0)
  *   in_shift  input index rotation: x[k] is read from fid[(k + in_shift) mod n_in]; requires n_in == n_out
  *   out_shift output index rotation: bin j is stored at (j + out_shift) mod n_out  (n_out/2 = fftshift)
- *   absmax_dev/argmax_dev  optional [batch]: max |S| (float) and its first index (in stored order) per spectrum
+ *   absmax_dev/argmax_dev  optional [batch]: max |S| (float) and its first index (in stored order) per spectrum;
+ *                          argmax_dev may be NULL (maxima only: the cheapest statistics pass)
  */
 int xmr_fid_to_spectrum_c64(const void* fid_dev, void* spec_dev, int64_t batch, int n_in, int n_out, int pad_left,
                             int window_mode, const float* window_dev, const float* win_rows_host, float scale,
@@ -80,7 +81,8 @@ int xmr_phase_each_c64(const void* in_dev, void* out_dev, int64_t batch, int n, 
                        const double* b_turns_dev, void* stream);
 
 /* Global first-occurrence argmax over a [batch] array of per-spectrum maxima (phasing.py:229-231).
- * Writes {max value, flat index = spectrum*n + argmax[spectrum]} to out_dev (float, then int64 at byte offset 8). */
+ * Writes {max value, flat index = spectrum*n + argmax[spectrum]} to out_dev (float, then int64 at byte offset 8);
+ * argmax_dev may be NULL (flat index = spectrum*n: the row only). */
 int xmr_global_argmax(const float* absmax_dev, const int* argmax_dev, int64_t batch, int n, void* out_dev,
                       void* stream);
 

@@ -65,10 +65,13 @@ def _win(geo, device):
 
 
 def local_stats(fid_t, geo):
-    """Pass 1 on this rank's shard.  Returns ``(max |S|, flat index)`` of the shard (host scalars)."""
-    _, absmax, argmax = D.fid_to_spectrum(fid_t, n_out=geo["n_out"], pad_left=geo["pad_left"],
-                                          window=_win(geo, fid_t.device), store=False, want_stats=True)
-    return D.global_argmax(absmax.reshape(-1), argmax.reshape(-1), geo["n_out"])
+    """Pass 1 on this rank's shard.  Returns ``(max |S|, row * n_out)`` of the shard (host scalars).
+
+    Only the per-spectrum maxima are recorded (the cheapest statistics pass); the position of the maximum inside the
+    winning row is recovered when that one row is transformed again for the search."""
+    _, absmax, _ = D.fid_to_spectrum(fid_t, n_out=geo["n_out"], pad_left=geo["pad_left"],
+                                     window=_win(geo, fid_t.device), store=False, want_stats=True, want_index=False)
+    return D.global_argmax(absmax.reshape(-1), None, geo["n_out"])
 
 
 def search_on_row(fid_row_t, geo, flat_index, method="acme", peak_width=0.5, target_coord=None, p0_only=False,
@@ -77,10 +80,10 @@ def search_on_row(fid_row_t, geo, flat_index, method="acme", peak_width=0.5, tar
     from .processing import _index_width, _smooth_slice
 
     n_out, freqs = geo["n_out"], geo["freqs"]
-    spec, _, _ = D.fid_to_spectrum(fid_row_t.reshape(1, -1), n_out=n_out, pad_left=geo["pad_left"],
-                                   window=_win(geo, fid_row_t.device))
+    spec, _, argmax = D.fid_to_spectrum(fid_row_t.reshape(1, -1), n_out=n_out, pad_left=geo["pad_left"],
+                                        window=_win(geo, fid_row_t.device), want_stats=True)
     work = spec.reshape(n_out)
-    argmax_idx = flat_index % n_out
+    argmax_idx = int(argmax.reshape(-1)[0].item())
     if target_coord is not None:
         target_idx = int(np.argmin(np.abs(freqs - target_coord)))
         pivot = float(target_coord)

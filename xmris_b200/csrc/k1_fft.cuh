@@ -64,10 +64,16 @@ __device__ __forceinline__ void amax_combine(float& v, int& i, float ov, int oi)
 }
 
 // WIN: 1 = full window table p.win[N]; 2 = separable p.win[column] * p.win_rows[row] (also "scale only").
-// The epilogue options (statistics, phase, store) are uniform run-time flags: p.absmax, p.phase_on, p.out.
-template <int N, bool INVERSE, int WIN, bool TMA>
+// FAST == 0: generic kernel; geometry (n_in, pad_left, shifts) and the epilogue options (statistics, phase, store) are
+//            uniform run-time values.
+// FAST != 0: specialised hot path for n_in == N, no padding, no input rotation, out_shift == N/2, with the epilogue
+//            fixed at compile time (bit mask of K1_FAST_*): no per-element predicates or index arithmetic.
+enum : int { K1_FAST_ON = 1, K1_FAST_STORE = 2, K1_FAST_STATS = 4, K1_FAST_PHASE = 8 };
+
+template <int N, bool INVERSE, int WIN, bool TMA, int FAST = 0>
 __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_kernel(const __grid_constant__ K1Params p) {
     using C = FftCfg<N>;
+    constexpr bool F = (FAST != 0);
     constexpr bool TW_PERSIST = (N <= 4096);
     constexpr int NTW = (C::R0 > 1) ? C::C0 * (C::R0 - 1) : 1;
 
@@ -82,8 +88,15 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
     const int t = tid % C::T;     // thread within the spectrum
 
     const long long ntiles = (p.batch + C::SPB - 1) / C::SPB;
-    const int n_in = p.n_in;
-    const bool need_load_barrier = (p.pad_left != 0) || ((p.in_shift % C::M) != 0);
+    const int n_in = F ? C::N : p.n_in;
+    const int pad_left = F ? 0 : p.pad_left;
+    const int in_shift = F ? 0 : p.in_shift;
+    const int out_shift = F ? C::N / 2 : p.out_shift;
+    const bool do_stats = F ? ((FAST & K1_FAST_STATS) != 0) : (p.absmax != nullptr);
+    const bool do_index = F ? false : (p.argmax != nullptr);      // the fast statistics pass records maxima only
+    const bool do_store = F ? ((FAST & K1_FAST_STORE) != 0) : (p.out != nullptr);
+    const bool do_phase = F ? ((FAST & K1_FAST_PHASE) != 0) : (p.phase_on != 0);
+    const bool need_load_barrier = (pad_left != 0) || ((in_shift % C::M) != 0);
 
     // ---- per-thread persistent state -------------------------------------------------------------------
     float2 tw_persist[TW_PERSIST ? NTW : 1];
@@ -97,7 +110,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
     float2 ph_base[C::C2];
 #pragma unroll
     for (int j = 0; j < C::C2; ++j) ph_base[j] = make_float2(1.f, 0.f);
-    if (p.phase_on) {
+    if (do_phase) {
 #pragma unroll
         for (int j = 0; j < C::C2; ++j) {
             const int q = t + C::T * j;
@@ -161,7 +174,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
 
         // ---- stage 0: load (zero-fill + window), R0-point DFTs, in-place exchange A --------------------
         float2 v[C::E];
-        stage0_load<C, WIN>(t, my_slot, valid ? n_in : 0, p.pad_left, p.in_shift, p.scale, p.win, wcol, p.win_rows, v);
+        stage0_load<C, WIN>(t, my_slot, (F || valid) ? n_in : 0, pad_left, in_shift, p.scale, p.win, wcol, p.win_rows, v);
         if (need_load_barrier) __syncthreads();
         stage0_store<C, INVERSE, TW_PERSIST>(t, my_slot, v, tw_persist, tw0_base);
         __syncthreads();
@@ -181,18 +194,23 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
 
         // ---- epilogue --------------------------------------------------------------------------------------
         constexpr int Q = C::R0 * C::R1;
-        if (p.absmax != nullptr) {
+        if (do_stats) {
             float best = -1.f;
             int besti = 0x7fffffff;
+            if (do_index) {
 #pragma unroll
-            for (int j = 0; j < C::C2; ++j)
+                for (int j = 0; j < C::C2; ++j)
 #pragma unroll
-                for (int d = 0; d < C::R2; ++d) {
-                    const float2 x = v[j * C::R2 + d];
-                    const float m2 = x.x * x.x + x.y * x.y;
-                    const int m = (t + C::T * j + Q * d + p.out_shift) & (C::N - 1);
-                    amax_combine(best, besti, m2, m);
-                }
+                    for (int d = 0; d < C::R2; ++d) {
+                        const float2 x = v[j * C::R2 + d];
+                        const float m2 = x.x * x.x + x.y * x.y;
+                        const int m = (t + C::T * j + Q * d + out_shift) & (C::N - 1);
+                        amax_combine(best, besti, m2, m);
+                    }
+            } else {
+#pragma unroll
+                for (int i = 0; i < C::E; ++i) best = fmaxf(best, v[i].x * v[i].x + v[i].y * v[i].y);
+            }
             constexpr int LANES = C::T < 32 ? C::T : 32;
 #pragma unroll
             for (int off = LANES / 2; off > 0; off >>= 1) {
@@ -212,19 +230,19 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
             }
             if (t == 0 && valid) {
                 p.absmax[spec] = sqrtf(best);
-                p.argmax[spec] = besti;
+                if (do_index) p.argmax[spec] = besti;
             }
         }
-        if (p.out != nullptr && valid) {
+        if (do_store && valid) {
             float2* dst = p.out + spec * (long long)C::N;
 #pragma unroll
             for (int j = 0; j < C::C2; ++j)
 #pragma unroll
                 for (int d = 0; d < C::R2; ++d) {
                     const int k = t + C::T * j + Q * d;
-                    const int m = (k + p.out_shift) & (C::N - 1);
+                    const int m = (k + out_shift) & (C::N - 1);
                     float2 x = v[j * C::R2 + d];
-                    if (p.phase_on) {
+                    if (do_phase) {
                         // m = q + Q*d' with d' = m / Q: rot = base(q) * step(d')
                         const float2 r = cmul(ph_base[j], p.ph_step[(m / Q) & 15]);
                         x = cmul(x, r);

@@ -7,10 +7,10 @@
 
 namespace xmr {
 
-template <int N, bool INVERSE, int WIN, bool TMA>
+template <int N, bool INVERSE, int WIN, bool TMA, int FAST = 0>
 static cudaError_t launch_one(const K1Params& p, int max_ctas, cudaStream_t st) {
     using C = FftCfg<N>;
-    auto kern = k1_kernel<N, INVERSE, WIN, TMA>;
+    auto kern = k1_kernel<N, INVERSE, WIN, TMA, FAST>;
     constexpr size_t smem = K1Smem<N>::TOTAL;
     static thread_local int cached_dev = -1;
     static thread_local int ctas_per_wave = 0;
@@ -45,6 +45,17 @@ cudaError_t XMR_CAT(k1_launch_, XMR_N)(const K1Params& p, bool inverse, int win,
     if (inverse) {
         // to_fid: no window (scale only -> separable mode with unit rows)
         return tma ? launch_one<XMR_N, true, 2, true>(p, max_ctas, st) : launch_one<XMR_N, true, 2, false>(p, max_ctas, st);
+    }
+    // hot path: full-length input, separable window, TMA, fftshift store -> compile-time epilogue variants
+    const bool fast_geom = tma && win == 2 && p.n_in == XMR_N && p.pad_left == 0 && p.in_shift == 0 &&
+                           p.out_shift == XMR_N / 2 && XMR_N >= 512;
+    if (fast_geom) {
+        const bool st_ = p.out != nullptr, stats = p.absmax != nullptr && p.argmax == nullptr, ph = p.phase_on != 0;
+        if (st_ && !stats && !ph && p.absmax == nullptr)
+            return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE>(p, max_ctas, st);
+        if (st_ && ph && p.absmax == nullptr)
+            return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE | K1_FAST_PHASE>(p, max_ctas, st);
+        if (!st_ && stats) return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STATS>(p, max_ctas, st);
     }
     if (win == 1)
         return tma ? launch_one<XMR_N, false, 1, true>(p, max_ctas, st) : launch_one<XMR_N, false, 1, false>(p, max_ctas, st);

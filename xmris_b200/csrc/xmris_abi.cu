@@ -141,7 +141,7 @@ __global__ void global_argmax_kernel(const float* __restrict__ absmax, const int
         for (int w = 1; w < int(blockDim.x >> 5); ++w)
             if (sv[w] > best || (sv[w] == best && si[w] < besti)) { best = sv[w]; besti = si[w]; }
         *reinterpret_cast<float*>(out) = best;
-        *reinterpret_cast<long long*>(out + 8) = (batch > 0) ? besti * n + argmax[besti] : -1;
+        *reinterpret_cast<long long*>(out + 8) = (batch > 0) ? besti * n + (argmax ? argmax[besti] : 0) : -1;
     }
 }
 
@@ -170,8 +170,8 @@ int xmr_fid_to_spectrum_c64(const void* fid_dev, void* spec_dev, int64_t batch, 
     if (batch == 0) return XMR_OK;
     if (!fid_dev) return fail(XMR_ERR_BAD_ARG, "fid_dev is NULL");
     if (!spec_dev && !absmax_dev) return fail(XMR_ERR_BAD_ARG, "nothing to do: spec_dev and absmax_dev are both NULL");
-    if ((absmax_dev == nullptr) != (argmax_dev == nullptr))
-        return fail(XMR_ERR_BAD_ARG, "absmax_dev and argmax_dev must be given together");
+    if (argmax_dev != nullptr && absmax_dev == nullptr)
+        return fail(XMR_ERR_BAD_ARG, "argmax_dev needs absmax_dev");
     if (in_shift != 0 && (n_in != n_out || pad_left != 0))
         return fail(XMR_ERR_BAD_ARG, "in_shift requires n_in == n_out and pad_left == 0");
     if (in_shift < 0 || in_shift >= n_out || out_shift < 0 || out_shift >= n_out)
@@ -286,7 +286,7 @@ int xmr_phase_each_c64(const void* in_dev, void* out_dev, int64_t batch, int n, 
 int xmr_global_argmax(const float* absmax_dev, const int* argmax_dev, int64_t batch, int n, void* out_dev,
                       void* stream) {
     if (batch < 0 || n < 1) return fail(XMR_ERR_BAD_ARG, "bad sizes");
-    if (!absmax_dev || !argmax_dev || !out_dev) return fail(XMR_ERR_BAD_ARG, "NULL pointer");
+    if (!absmax_dev || !out_dev) return fail(XMR_ERR_BAD_ARG, "NULL pointer");
     global_argmax_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(absmax_dev, argmax_dev, batch, n,
                                                                              static_cast<unsigned char*>(out_dev));
     cudaError_t e = cudaGetLastError();

@@ -97,7 +97,7 @@ class PreparedWindow:
 
 
 def fid_to_spectrum(fid, n_out=None, pad_left=0, window=None, scale=None, inverse=False, in_shift=0, out_shift=None,
-                    want_stats=False, phase_turns=None, out=None, store=True, stream=None):
+                    want_stats=False, phase_turns=None, out=None, store=True, stream=None, want_index=True):
     """Fused zero-fill -> window -> FFT -> shift [-> phase] on the device.
 
     fid          complex64 CUDA tensor ``[..., n_in]``
@@ -133,7 +133,8 @@ def fid_to_spectrum(fid, n_out=None, pad_left=0, window=None, scale=None, invers
     absmax = argmax = None
     if want_stats:
         absmax = torch.empty(batch_shape, dtype=torch.float32, device=dev)
-        argmax = torch.empty(batch_shape, dtype=torch.int32, device=dev)
+        if want_index:
+            argmax = torch.empty(batch_shape, dtype=torch.int32, device=dev)
     win_mode, win_dev, rows = _lib.WIN_NONE, None, None
     if isinstance(window, PreparedWindow):
         if window.n_out != n_out or window.device != dev:
@@ -222,7 +223,9 @@ def phase_each(x, a_turns, b_turns, stream=None):
 
 
 def global_argmax(absmax, argmax, n, stream=None):
-    """First-occurrence global argmax over per-spectrum maxima.  Returns ``(max_value, flat_index)`` (host sync)."""
+    """First-occurrence global argmax over per-spectrum maxima.  Returns ``(max_value, flat_index)`` (host sync).
+
+    ``argmax=None``: only the winning row is wanted; the flat index is ``row * n``."""
     torch = _torch()
     lib = _lib.load()
     out = torch.zeros(16, dtype=torch.uint8, device=absmax.device)

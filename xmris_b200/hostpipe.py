@@ -62,11 +62,10 @@ class HostChain:
             with torch.cuda.stream(self.s_cmp):
                 for (lo, hi), ev in zip(chunks, in_done):       # pass 1 trails the copies chunk by chunk
                     self.s_cmp.wait_event(ev)
-                    _, am, ai = D.fid_to_spectrum(self.d_in[lo:hi], n_out=self.n_out, pad_left=geo["pad_left"], window=win,
-                                                  store=False, want_stats=True)
+                    _, am, _ = D.fid_to_spectrum(self.d_in[lo:hi], n_out=self.n_out, pad_left=geo["pad_left"], window=win,
+                                                 store=False, want_stats=True, want_index=False)
                     self.absmax[lo:hi].copy_(am, non_blocking=True)
-                    self.argmax[lo:hi].copy_(ai, non_blocking=True)
-                vmax, findex = D.global_argmax(self.absmax, self.argmax, self.n_out)
+                vmax, findex = D.global_argmax(self.absmax, None, self.n_out)
 
                 def search():
                     return chain.search_on_row(self.d_in[findex // self.n_out], geo, findex, self.method, self.peak_width,
