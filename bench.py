@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=1 << 20, help="voxels per GPU")
     ap.add_argument("--e2e-batch", type=int, default=1 << 16, help="voxels per GPU for the host-buffer (e2e) leg")
     ap.add_argument("--cpu-sample", type=int, default=16384, help="voxels of the CPU baseline sample")
+    ap.add_argument("--ref-sample", type=int, default=65536, help="voxels per step of the --impl reference arm")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -61,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -71,12 +72,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark(self):
+        """Index of the next sample: call at the start of the timed region (the sampler is started before warm-up)."""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = self.rows[getattr(self, "first", 0):] or self.rows[-1:]
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -93,39 +100,29 @@ class ClockSampler:
 # CPU baseline / reference arm: the oracle (numpy/scipy restatement of the reference's own path)
 # ---------------------------------------------------------------------------------------------------------
 
-_W = {}
-
-
-def _cpu_worker_init(seed_base, rows, n_points):
+def _cpu_worker(conn, seed, rows, n_points):
+    """One host process of the reference arm: owns a block of voxels and serves the chain's whole-array steps."""
+    from oracle import xmris_oracle as orc
     from xmris_b200.synth import make_fids_numpy
 
-    wid = os.getpid()
-    fid, t, _ = make_fids_numpy("1H", rows, n_points, seed=seed_base + (wid % 9973))
-    _W["fid"], _W["t"] = fid, t
-
-
-def _cpu_pass_a(_):
-    """zero_fill -> apodize_exp -> to_spectrum on this worker's block + local argmax (phasing.py:229-231)."""
-    from oracle import xmris_oracle as orc
-
-    spec, freqs = orc.chain_to_spectrum(_W["fid"], 1, _W["t"], None, "end", LB)
-    _W["spec"], _W["freqs"] = spec, freqs
-    a = np.abs(spec)
-    flat = int(np.argmax(a))
-    return os.getpid(), float(a.ravel()[flat]), flat
-
-
-def _cpu_get_row(args):
-    pid, row = args
-    return _W["spec"][row].copy() if os.getpid() == pid else None
-
-
-def _cpu_pass_b(args):
-    from oracle import xmris_oracle as orc
-
-    p0, p1, pivot = args
-    out, _ = orc.phase(_W["spec"], 1, _W["freqs"], p0, p1, pivot)
-    return float(np.abs(out[0, 0]))
+    fid, t, _ = make_fids_numpy("1H", rows, n_points, seed=seed)
+    spec = freqs = None
+    conn.send("ready")
+    while True:
+        cmd = conn.recv()
+        if cmd[0] == "pass_a":      # zero_fill -> apodize_exp -> to_spectrum + local argmax (phasing.py:229-231)
+            spec, freqs = orc.chain_to_spectrum(fid, 1, t, None, "end", LB)
+            a = np.abs(spec)
+            flat = int(np.argmax(a))
+            conn.send((float(a.ravel()[flat]), flat))
+        elif cmd[0] == "row":
+            conn.send((spec[cmd[1]].copy(), freqs))
+        elif cmd[0] == "pass_b":    # phase() on the whole block (phasing.py:290)
+            out, _ = orc.phase(spec, 1, freqs, cmd[1], cmd[2], cmd[3])
+            conn.send(float(np.abs(out[0, 0])))
+        else:
+            conn.close()
+            return
 
 
 def cpu_chain_single_process(n_spectra, n_points):
@@ -141,38 +138,52 @@ def cpu_chain_single_process(n_spectra, n_points):
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path with all host cores (voxel blocks in a
-    process pool; the single DE search of mode="single" runs once on the winning spectrum)."""
+    """--impl reference: the reference's CPU implementation of the path with all host cores (voxel blocks in worker
+    processes; the single DE search of mode="single" runs once on the winning spectrum, as in phasing.py:276-290)."""
     import multiprocessing as mp
 
     from oracle import xmris_oracle as orc
 
     cores = len(os.sched_getaffinity(0))
     workers = max(1, min(cores, 64))
-    rows = max(64, args.cpu_sample // workers)
+    rows = max(64, args.ref_sample // workers)
     ctx = mp.get_context("fork")
+    conns, procs = [], []
+    for w in range(workers):
+        parent, child = ctx.Pipe()
+        pr = ctx.Process(target=_cpu_worker, args=(child, 1000 + w, rows, N_POINTS), daemon=True)
+        pr.start()
+        conns.append(parent)
+        procs.append(pr)
+    for c in conns:
+        assert c.recv() == "ready"
+
+    def step():
+        for c in conns:
+            c.send(("pass_a",))
+        res = [c.recv() for c in conns]
+        win = max(range(workers), key=lambda i: (res[i][0], -i))
+        row, idx = divmod(res[win][1], N_POINTS)
+        conns[win].send(("row", row))
+        spec1d, freqs = conns[win].recv()
+        pivot = float(freqs[idx])
+        p0, p1, _ = orc.autophase_search(spec1d, freqs, pivot, "acme", idx, 1, False)
+        for c in conns:
+            c.send(("pass_b", p0, p1, pivot))
+        for c in conns:
+            c.recv()
+
     times = []
-    with ctx.Pool(workers, initializer=_cpu_worker_init, initargs=(1000, rows, N_POINTS)) as pool:
-        def step():
-            res = pool.map(_cpu_pass_a, range(workers), chunksize=1)
-            best = max(res, key=lambda r: r[1])
-            pid, _, flat = best
-            row, idx = divmod(flat, N_POINTS)
-            got = [r for r in pool.map(_cpu_get_row, [(pid, row)] * (workers * 4), chunksize=1) if r is not None]
-            if not got:
-                return None
-            spec1d = got[0]
-            freqs = np.roll(np.fft.fftfreq(N_POINTS, d=1.0 / 5000.0), N_POINTS // 2)
-            pivot = float(freqs[idx])
-            p0, p1, _ = orc.autophase_search(spec1d, freqs, pivot, "acme", idx, 1, False)
-            pool.map(_cpu_pass_b, [(p0, p1, pivot)] * workers, chunksize=1)
-            return True
-        for _ in range(args.warmup):
-            step()
-        for _ in range(args.steps):
-            t0 = time.perf_counter()
-            step()
-            times.append(time.perf_counter() - t0)
+    for _ in range(args.warmup):
+        step()
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    for c in conns:
+        c.send(("quit",))
+    for pr in procs:
+        pr.join(timeout=10)
     total = rows * workers
     ms = 1e3 * float(np.mean(times))
     value = total / (ms / 1e3)
@@ -261,12 +272,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler.mark()
     launches["n"] = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
