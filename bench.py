@@ -338,8 +338,13 @@ def run_ours(args):
     achieved = b_alg / (dom_ms / 1e3) / 1e9
     chain_achieved = b_alg / (ms_step / 1e3) / 1e9
     dominant = "k1_kernel<4096> store+phase (pass 2)" if args.mode == "single" else "k2 per-voxel chain kernel"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if args.mode == "single" and os.path.isfile(tpath):
+        tj = json.load(open(tpath))    # bytes/spectrum from the committed ncu --set full capture, scaled to this launch
+        traffic = (tj["dram_bytes_read_per_spectrum"] + tj["dram_bytes_write_per_spectrum"]) * batch
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": dominant, "kernel_ms": dom_ms, "peak_source": peak_src,
+                "traffic": traffic, "algorithmic_bytes": b_alg, "kernel": dominant, "kernel_ms": dom_ms, "peak_source": peak_src,
                 "chain_achieved": chain_achieved, "chain_frac": chain_achieved / peak,
                 "note": "achieved = 8*(n_in+n_out)*batch / kernel time; chain_* uses the whole step "
                         "(mode=single must read the FID twice: compulsory 8*(2*n_in+n_out))"}

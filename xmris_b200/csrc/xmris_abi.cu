@@ -1,4 +1,5 @@
 // C ABI of libxmris_b200.so (see include/xmris_b200.h) + the small elementwise / reduction kernels.
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -117,29 +118,43 @@ __global__ void phase_each_kernel(const float2* __restrict__ in, float2* __restr
     }
 }
 
-__global__ void global_argmax_kernel(const float* __restrict__ absmax, const int* __restrict__ argmax, long long batch,
-                                     int n, unsigned char* out) {
+// Two-level first-occurrence argmax: stage 1 reduces strided slices to per-block candidates, stage 2 (one block)
+// merges them.  Ties resolve to the lowest row index (numpy argmax order, phasing.py:229-231).
+__device__ __forceinline__ void argmax_merge(float& v, long long& i, float ov, long long oi) {
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+}
+__device__ __forceinline__ void argmax_block(float& best, long long& besti) {
     __shared__ float sv[32];
     __shared__ long long si[32];
-    float best = -1.f;
-    long long besti = 0x7fffffffffffffffLL;
-    for (long long b = threadIdx.x; b < batch; b += blockDim.x) {
-        const float v = absmax[b];
-        if (v > best) {   // ascending scan: strict '>' keeps the first occurrence
-            best = v;
-            besti = b;
-        }
-    }
     for (int off = 16; off > 0; off >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, best, off);
         const long long oi = __shfl_xor_sync(0xffffffffu, besti, off);
-        if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+        argmax_merge(best, besti, ov, oi);
     }
     if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = besti; }
     __syncthreads();
+    if (threadIdx.x == 0)
+        for (int w = 1; w < int(blockDim.x >> 5); ++w) argmax_merge(best, besti, sv[w], si[w]);
+}
+constexpr int ARGMAX_BLOCKS = 256;
+__device__ float g_part_v[8][ARGMAX_BLOCKS];          // indexed by a small stream-slot to keep concurrent calls apart
+__device__ long long g_part_i[8][ARGMAX_BLOCKS];
+
+__global__ void global_argmax_stage1(const float* __restrict__ absmax, long long batch, int slot) {
+    float best = -1.f;
+    long long besti = 0x7fffffffffffffffLL;
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < batch; b += (long long)gridDim.x * blockDim.x)
+        argmax_merge(best, besti, absmax[b], b);
+    argmax_block(best, besti);
+    if (threadIdx.x == 0) { g_part_v[slot][blockIdx.x] = best; g_part_i[slot][blockIdx.x] = besti; }
+}
+__global__ void global_argmax_kernel(const float* __restrict__ absmax, const int* __restrict__ argmax, long long batch,
+                                     int n, unsigned char* out, int nparts, int slot) {
+    float best = -1.f;
+    long long besti = 0x7fffffffffffffffLL;
+    for (int b = threadIdx.x; b < nparts; b += blockDim.x) argmax_merge(best, besti, g_part_v[slot][b], g_part_i[slot][b]);
+    argmax_block(best, besti);
     if (threadIdx.x == 0) {
-        for (int w = 1; w < int(blockDim.x >> 5); ++w)
-            if (sv[w] > best || (sv[w] == best && si[w] < besti)) { best = sv[w]; besti = si[w]; }
         *reinterpret_cast<float*>(out) = best;
         *reinterpret_cast<long long*>(out + 8) = (batch > 0) ? besti * n + (argmax ? argmax[besti] : 0) : -1;
     }
@@ -287,8 +302,14 @@ int xmr_global_argmax(const float* absmax_dev, const int* argmax_dev, int64_t ba
                       void* stream) {
     if (batch < 0 || n < 1) return fail(XMR_ERR_BAD_ARG, "bad sizes");
     if (!absmax_dev || !out_dev) return fail(XMR_ERR_BAD_ARG, "NULL pointer");
-    global_argmax_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(absmax_dev, argmax_dev, batch, n,
-                                                                             static_cast<unsigned char*>(out_dev));
+    static std::atomic<unsigned> counter{0};
+    const int slot = int(counter.fetch_add(1) & 7u);   // partials of up to 8 in-flight calls never collide
+    long long blocks = (batch + 1023) / 1024;
+    if (blocks > ARGMAX_BLOCKS) blocks = ARGMAX_BLOCKS;
+    if (blocks < 1) blocks = 1;
+    global_argmax_stage1<<<int(blocks), 1024, 0, static_cast<cudaStream_t>(stream)>>>(absmax_dev, batch, slot);
+    global_argmax_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(absmax_dev, argmax_dev, batch, n,
+                                                                           static_cast<unsigned char*>(out_dev), int(blocks), slot);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? XMR_OK : cuda_fail(e, "global_argmax launch");
 }
