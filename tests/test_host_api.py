@@ -178,3 +178,24 @@ def test_two_rank_exchange_gloo():
     # rank 1 holds the global maximum: only it searches, both ranks receive its answer
     assert got[0][1] == got[1][1] == (2.5, 2.5, 3.5, 4.5)
     assert got[0][2] == [] and got[1][2] == [1]
+
+
+def test_to_ppm_to_hz_coordinates_only():
+    # reference tests/test_core.py:642-714 and docs/notebooks/basics/hz_and_ppm.md:169-203
+    hz = np.linspace(-500, 500, 11)
+    da = xr.DataArray(np.arange(22.0).reshape(2, 11), dims=["voxel", "frequency"], coords={"frequency": hz},
+                      attrs={"reference_frequency": 123.2, "carrier_ppm": 4.7, "keep": 1})
+    ppm = da.xmr.to_ppm()
+    assert ppm.dims == ("voxel", "chemical_shift") and ppm.attrs == da.attrs
+    np.testing.assert_allclose(ppm.coords["chemical_shift"].values, 4.7 + hz / 123.2)
+    assert ppm.coords["chemical_shift"].attrs == {"long_name": "Chemical Shift"}
+    np.testing.assert_array_equal(ppm.coords["frequency"].values, hz)       # old axis kept as a non-index coordinate
+    np.testing.assert_array_equal(ppm.values, da.values)
+    back = ppm.xmr.to_hz()
+    assert back.dims == ("voxel", "frequency")
+    np.testing.assert_allclose(back.coords["frequency"].values, hz, atol=1e-9)
+    assert back.coords["frequency"].attrs == {"long_name": "Frequency", "units": "Hz"}
+    with pytest.raises(ValueError, match="requires the following missing attributes"):
+        xr.DataArray(np.zeros(3), dims=["frequency"], coords={"frequency": np.arange(3.0)}).xmr.to_ppm()
+    with pytest.raises(ValueError, match="missing dimension"):
+        da.xmr.to_ppm(dim="nope")

@@ -19,6 +19,13 @@ class XmrisB200Accessor:
     def __init__(self, xarray_obj):
         self._obj = xarray_obj
 
+    # --- coordinate systems (accessor.py:329-366; host metadata only) ---
+    def to_ppm(self, dim: str = DIMS.frequency):
+        return P.to_ppm(self._obj, dim=dim)
+
+    def to_hz(self, dim: str = DIMS.chemical_shift):
+        return P.to_hz(self._obj, dim=dim)
+
     # --- processing (accessor.py:452-550) ---
     def apodize_exp(self, dim: str = DIMS.time, lb: float = 1.0):
         return P.apodize_exp(self._obj, dim=dim, lb=lb)

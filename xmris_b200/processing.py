@@ -231,6 +231,41 @@ def to_fid(da, dim: str = DIMS.frequency, out_dim: str = DIMS.time):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# N3 to_ppm / to_hz -- coordinate-only, host metadata          reference: core/accessor.py:329-366
+# ---------------------------------------------------------------------------------------------------------
+
+
+def _require_attrs(da, method_name, *keys):
+    """``@requires_attrs`` (``core/validation.py:26-60``): same ValueError text."""
+    missing = [k for k in keys if k not in da.attrs]
+    if missing:
+        raise ValueError(
+            f"Method '{method_name}' requires the following missing attributes "
+            f"in `obj.attrs`: {missing}.\n\n"
+            f"To fix this, assign them using standard xarray methods:\n"
+            f"    >>> obj = obj.assign_attrs({{{repr(missing[0])}: value}})"
+        )
+
+
+def to_ppm(da, dim: str = DIMS.frequency):
+    """Relative frequency axis [Hz] -> absolute chemical shift axis [ppm] (``accessor.py:332-348``); no data touched."""
+    _require_attrs(da, "to_ppm", ATTRS.reference_frequency, ATTRS.carrier_ppm)
+    _check_dims(da, dim, "to_ppm")
+    ppm = da.attrs[ATTRS.carrier_ppm] + (np.asarray(da.coords[dim].values) / da.attrs[ATTRS.reference_frequency])
+    var = as_variable(DIMS.chemical_shift, dim, ppm)
+    return da.assign_coords({DIMS.chemical_shift: var}).swap_dims({dim: DIMS.chemical_shift})
+
+
+def to_hz(da, dim: str = DIMS.chemical_shift):
+    """Absolute chemical shift axis [ppm] -> relative frequency axis [Hz] (``accessor.py:350-366``)."""
+    _require_attrs(da, "to_hz", ATTRS.reference_frequency, ATTRS.carrier_ppm)
+    _check_dims(da, dim, "to_hz")
+    hz = (np.asarray(da.coords[dim].values) - da.attrs[ATTRS.carrier_ppm]) * da.attrs[ATTRS.reference_frequency]
+    var = as_variable(COORDS.frequency, dim, hz)
+    return da.assign_coords({COORDS.frequency: var}).swap_dims({dim: DIMS.frequency})
+
+
+# ---------------------------------------------------------------------------------------------------------
 # A4 phase                                                          reference: processing/phasing.py:10-96
 # ---------------------------------------------------------------------------------------------------------
 

@@ -22,6 +22,8 @@ class XmrisTerm(str):
 
 
 class _Attrs:
+    reference_frequency = XmrisTerm("reference_frequency", "Measured Larmor frequency of the target nucleus.", "MHz")
+    carrier_ppm = XmrisTerm("carrier_ppm", "Absolute chemical shift at 0 Hz of the baseband signal.", "ppm")
     phase_p0 = XmrisTerm("phase_p0", "Zero-order phase angle applied.", "degrees")
     phase_p1 = XmrisTerm("phase_p1", "First-order phase angle applied.", "degrees")
     phase_pivot = XmrisTerm("phase_pivot", "Coordinate value the first-order phase is anchored at.", "dimension-dependent")

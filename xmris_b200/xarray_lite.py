@@ -302,6 +302,21 @@ class DataArray:
             return self._replace(dims=dims, coords=co)
         return self._replace(name=new_name_or_name_dict)
 
+    def swap_dims(self, dims_dict=None, **kw):
+        """Make another 1-D coordinate the dimension (index) coordinate; the old one stays as a non-index coord."""
+        mapping = dict(dims_dict or {})
+        mapping.update(kw)
+        for old, new in mapping.items():
+            if old not in self._dims:
+                raise ValueError(f"cannot swap from dimension {old!r} because it is not one of the dimensions {self._dims}")
+            if new in self._coords and self._coords[new].dims != (old,):
+                raise ValueError(f"replacement dimension {new!r} is not a 1D variable along the old dimension {old!r}")
+        dims = tuple(mapping.get(d, d) for d in self._dims)
+        co = OrderedDict()
+        for k, v in self._coords.items():
+            co[k] = Variable(tuple(mapping.get(d, d) for d in v.dims), v._data, v.attrs)
+        return self._replace(dims=dims, coords=co)
+
     def pipe(self, func, *args, **kwargs):
         return func(self, *args, **kwargs)
 
