@@ -15,6 +15,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "autophase_eval.cuh"
 #include "fft_stages.cuh"
 #include "k1_fft.cuh"
@@ -28,6 +30,7 @@ constexpr int K2_NP0 = 24;       // coarse p0: -180 + 15*k
 constexpr int K2_NP1 = 179;      // coarse p1: -4000 + 45*k (last clamped to 4000)
 constexpr int K2_NSTART = 6;
 constexpr int K2_NROUND = 7;
+constexpr int K2_NSHORT = 64;     // coarse cells re-evaluated at the finer subsample
 constexpr int K2_NP0_ONLY = 121; // p0_only coarse: -180 + 3*k
 constexpr int K2_PPL_SHIFT = 5;   // log2(pairs per lane) for N = 4096; other N: any padding works, 4096 is conflict-free
 
@@ -68,7 +71,7 @@ struct K2Smem {
     static constexpr size_t SUBP = size_t(C::N / K2_SUB + (C::N / K2_SUB >> K2_PPL_SHIFT) + 2) * sizeof(float4);
     static constexpr size_t CELLS = size_t(K2_NP1) * (K2_NP0 / K2_K);         // (p1, chunk) cells
     static constexpr size_t F = ((CELLS > 32 ? CELLS : 32) * 8 + 15) / 16 * 16; // {float f, int k} per cell
-    static constexpr size_t MISC = 1024;
+    static constexpr size_t MISC = 2048;
     static constexpr size_t TOTAL = SLOT + B + SUBP + F + MISC;
 };
 
@@ -78,7 +81,7 @@ struct K2Start {
 };
 
 // ACME on the stride-SUB pair subsample: pair j holds (S[SUB*j], S[SUB*j+1]).
-template <int K>
+template <int K, int STRIDE = 1>
 __device__ __forceinline__ void lane_accumulate_pairs(const float4* __restrict__ sub, int j0, int j1, float tpu,
                                                       float u0, float du, const float (&c0)[K], const float (&s0)[K],
                                                       Acc<float, METHOD_ACME, K>& acc) {
@@ -91,12 +94,12 @@ __device__ __forceinline__ void lane_accumulate_pairs(const float4* __restrict__
         float ti = tpu * du;
         ti -= floorf(ti);
         sincospif(2.0f * ti, &s1, &c1);
-        float ts = tpu * du * float(K2_SUB);
+        float ts = tpu * du * float(K2_SUB * STRIDE);
         ts -= floorf(ts);
         sincospif(2.0f * ts, &ss, &cs);
     }
 #pragma unroll 2
-    for (int j = j0; j < j1; ++j) {
+    for (int j = j0; j < j1; j += STRIDE) {
         const float4 q = sub[j + (j >> K2_PPL_SHIFT)];                           // one pad element per lane chunk
         const float ax = q.x * cr - q.y * sr, ay = q.x * sr + q.y * cr;           // w at m
         const float r1c = cr * c1 - sr * s1, r1s = cr * s1 + sr * c1;            // rotation at m+1
@@ -141,10 +144,15 @@ k2_kernel(const __grid_constant__ K2Params p) {
     float* redv = reinterpret_cast<float*>(misc + 16);                     // [32]
     int* redi = reinterpret_cast<int*>(misc + 16 + 128);                   // [32]
     K2Start* starts = reinterpret_cast<K2Start*>(misc + 16 + 256);         // [NSTART]
-    float* rowf = reinterpret_cast<float*>(misc + 16 + 256 + 128);         // [8] per-row best f
-    float* rowp0 = rowf + 8;                                               // [8]
-    float* rowp1 = rowf + 16;                                              // [8]
-    float* bcast = rowf + 24;                                              // [8] centre broadcast
+    float* rowf = reinterpret_cast<float*>(misc + 16 + 256 + 128);         // scratch base
+    float* st_p0 = rowf + 32;                                              // [NSTART] per-start centre / value / flag
+    float* st_p1 = st_p0 + 8;
+    float* st_f = st_p0 + 16;
+    int* st_on = reinterpret_cast<int*>(st_p0 + 24);
+    float* rf = st_p0 + 32;                                                // [NSTART*8] per-(start,row) results
+    float* rp0 = rf + K2_NSTART * 8;
+    float* rp1 = rp0 + K2_NSTART * 8;
+    int* shortlist = reinterpret_cast<int*>(rp1 + K2_NSTART * 8);           // [K2_NSHORT]
 
     const int t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5;
@@ -288,7 +296,9 @@ k2_kernel(const __grid_constant__ K2Params p) {
         const int nchunk = (np0 + K2_K - 1) / K2_K;
         const int np1 = p.p0_only ? 1 : K2_NP1;
         const int ncell = np1 * nchunk;
-        for (int cell = warp; cell < ncell; cell += WPS) {
+        // evaluates one (p1, chunk of 8 p0) cell on the pair subsample (ACME; every STRIDE-th pair) or on the ROI
+        auto eval_cell = [&](int cell, auto stride_tag) {
+            constexpr int STRIDE = decltype(stride_tag)::value;
             const int i1 = cell / nchunk, ch = cell - i1 * nchunk;
             const float p1 = p.p0_only ? 0.f : fminf(-4000.f + 45.f * float(i1), 4000.f);
             const float tpu = p1 * (1.0f / 360.0f);
@@ -302,7 +312,7 @@ k2_kernel(const __grid_constant__ K2Params p) {
             acc.init();
             if constexpr (METHOD == METHOD_ACME) {
                 constexpr int PPL = (N / K2_SUB) / 32;   // pairs per lane
-                lane_accumulate_pairs<K2_K>(subp, lane * PPL, (lane + 1) * PPL, tpu, u0, duf, c0, s0, acc);
+                lane_accumulate_pairs<K2_K, STRIDE>(subp, lane * PPL, (lane + 1) * PPL, tpu, u0, duf, c0, s0, acc);
             } else {
                 lane_accumulate_rt<float, METHOD, K2_K>(sp, PADSHIFT, lane * L, (lane + 1) * L, geom, tpu, u0, duf, c0, s0, acc);
             }
@@ -318,9 +328,9 @@ k2_kernel(const __grid_constant__ K2Params p) {
                 const float wx = Spiv.x * cs - Spiv.y * sn, wy = Spiv.x * sn + Spiv.y * cs;
 #pragma unroll
                 for (int k = 0; k < K2_K; ++k) {
-                    acc.a[k][0] *= float(K2_SUB);
-                    acc.a[k][1] *= float(K2_SUB);
-                    acc.a[k][2] *= float(K2_SUB);
+                    acc.a[k][0] *= float(K2_SUB * STRIDE);
+                    acc.a[k][1] *= float(K2_SUB * STRIDE);
+                    acc.a[k][2] *= float(K2_SUB * STRIDE);
                     acc.a[k][3] = fmaxf(acc.a[k][3], wx * c0[k] - wy * s0[k]);
                 }
             }
@@ -330,6 +340,42 @@ k2_kernel(const __grid_constant__ K2Params p) {
                 if (ch * K2_K + k < np0 && f < bf) { bf = f; bk = k; }
             }
             if (lane == 0) { cellf[cell] = bf; cellk[cell] = bk; }
+        };
+        const bool two_level = (METHOD == METHOD_ACME) && (ncell > K2_NSHORT);
+        if (two_level) {
+            // level 1: every 16th point pair on all cells; level 2: the K2_NSHORT best cells again on every 4th pair
+            for (int cell = warp; cell < ncell; cell += WPS) eval_cell(cell, std::integral_constant<int, 4>{});
+            __syncthreads();
+            if (warp == 0) {
+                for (int i = 0; i < K2_NSHORT; ++i) {
+                    float bf = CUDART_INF_F;
+                    int bc = 0x7fffffff;
+                    for (int c = lane; c < ncell; c += 32) {
+                        const float f = cellf[c];
+                        if (f < bf || (f == bf && c < bc)) { bf = f; bc = c; }
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const float of = __shfl_xor_sync(0xffffffffu, bf, off);
+                        const int oc = __shfl_xor_sync(0xffffffffu, bc, off);
+                        if (of < bf || (of == bf && oc < bc)) { bf = of; bc = oc; }
+                    }
+                    if (bc == 0x7fffffff) bc = -1;      // fewer finite cells than the short list
+                    if (lane == 0) {
+                        shortlist[i] = bc;
+                        if (bc >= 0) cellf[bc] = CUDART_INF_F;
+                    }
+                    __syncwarp();
+                }
+                for (int c = lane; c < ncell; c += 32) cellf[c] = CUDART_INF_F;   // only re-evaluated cells compete
+            }
+            __syncthreads();
+            for (int i = warp; i < K2_NSHORT; i += WPS) {
+                const int cell = shortlist[i];
+                if (cell >= 0) eval_cell(cell, std::integral_constant<int, 1>{});
+            }
+        } else {
+            for (int cell = warp; cell < ncell; cell += WPS) eval_cell(cell, std::integral_constant<int, 1>{});
         }
         __syncthreads();
 
@@ -368,54 +414,122 @@ k2_kernel(const __grid_constant__ K2Params p) {
         }
         __syncthreads();
 
-        float fin_f = CUDART_INF_F, fin_p0 = 0.f, fin_p1 = 0.f;
-        for (int s = 0; s < K2_NSTART; ++s) {
-            float c0c = starts[s].p0, c1c = starts[s].p1, fbest = CUDART_INF_F;
-            float h0 = p0step, h1 = p.p0_only ? 0.f : 45.f;
-            if (!(starts[s].f < CUDART_INF_F)) continue;     // uniform across the CTA (shared value)
-            for (int round = 0; round < K2_NROUND; ++round) {
-                float rbf = CUDART_INF_F, rb0 = c0c, rb1 = c1c;
-                for (int row = warp; row < 8; row += WPS) {
-                    if (p.p0_only && row > 0) break;
-                    const float off1 = (float(2 * row) - 7.f) * (1.f / 7.f);
-                    const float p1 = p.p0_only ? 0.f : fminf(fmaxf(c1c + off1 * h1, -4000.f), 4000.f);
-                    float c0[K2_K], s0[K2_K], p0k[K2_K];
-#pragma unroll
-                    for (int k = 0; k < K2_K; ++k) {
-                        // p0 is periodic: candidates leaving the closed box [-180, 180] re-enter on the other side
-                        float q0 = c0c + (float(2 * k) - 7.f) * (1.f / 7.f) * h0;
-                        q0 = q0 > 180.f ? q0 - 360.f : (q0 < -180.f ? q0 + 360.f : q0);
-                        p0k[k] = q0;
-                        sincospif(p0k[k] * (1.0f / 180.0f), &s0[k], &c0[k]);
-                    }
-                    Acc<float, METHOD, K2_K> acc;
-                    acc.init();
-                    lane_accumulate_rt<float, METHOD, K2_K>(sp, PADSHIFT, lane * L, (lane + 1) * L, geom, p1 * (1.0f / 360.0f),
-                                                            u0, duf, c0, s0, acc);
-                    acc.warp_reduce();
-#pragma unroll
-                    for (int k = 0; k < K2_K; ++k) {
-                        const float f = acc.score(k, geom);
-                        if (f < rbf) { rbf = f; rb0 = p0k[k]; rb1 = p1; }
-                    }
-                }
-                if (lane == 0 && warp < 8) { rowf[warp] = rbf; rowp0[warp] = rb0; rowp1[warp] = rb1; }
-                __syncthreads();
+        // Zoom refinement with successive pruning.  Every round evaluates, for each active start, an 8x8 window
+        // (8 p1 rows x 8 p0) around its current centre; rows of all active starts are spread over the warps.
+        //   rounds 0-1: all NSTART starts        (window +-15 x +-45 deg -> +-1.5 x +-4.6 deg)
+        //   rounds 2-3: the best 3 distinct starts
+        //   rounds 4-6: the best 2                (final spacing 0.005 x 0.014 deg)
+        // All rounds use the FULL spectrum: the pair subsample only localises basins -- its noise-induced fine structure
+        // (local minima every ~25 deg of p1) differs from the full objective's, so it must not steer the refinement.
+        if (t < K2_NSTART) {
+            st_p0[t] = starts[t].p0;
+            st_p1[t] = starts[t].p1;
+            st_f[t] = CUDART_INF_F;
+            st_on[t] = (starts[t].f < CUDART_INF_F) ? 1 : 0;
+        }
+        __syncthreads();
+        float h0 = p0step, h1 = p.p0_only ? 0.f : 45.f;
+        for (int round = 0; round < K2_NROUND; ++round) {
+            const bool use_pairs = false;
+            if (round == 2 || round == 4) {
+                // prune: keep the best `keep` starts that are not duplicates of a better one
                 if (t == 0) {
-                    float bf = fbest, b0 = c0c, b1 = c1c;
-                    const int nrow = WPS < 8 ? WPS : 8;
-                    for (int w = 0; w < nrow; ++w)
-                        if (rowf[w] < bf) { bf = rowf[w]; b0 = rowp0[w]; b1 = rowp1[w]; }
-                    bcast[0] = bf; bcast[1] = b0; bcast[2] = b1;
+                    const int keep = (round == 2) ? 3 : 2;
+                    int kept = 0;
+                    bool used[K2_NSTART];
+                    for (int i = 0; i < K2_NSTART; ++i) used[i] = false;
+                    int order[K2_NSTART];
+                    for (int r = 0; r < K2_NSTART; ++r) {
+                        int bi = -1;
+                        for (int i = 0; i < K2_NSTART; ++i)
+                            if (!used[i] && st_on[i] && (bi < 0 || st_f[i] < st_f[bi])) bi = i;
+                        order[r] = bi;
+                        if (bi >= 0) used[bi] = true;
+                    }
+                    for (int r = 0; r < K2_NSTART; ++r) {
+                        const int i = order[r];
+                        if (i < 0) continue;
+                        bool dup = false;
+                        for (int q = 0; q < r; ++q) {
+                            const int j = order[q];
+                            if (j >= 0 && st_on[j] && fabsf(st_p0[i] - st_p0[j]) < 4.f * h0 && fabsf(st_p1[i] - st_p1[j]) < 4.f * h1)
+                                dup = true;
+                        }
+                        if (dup || kept >= keep) st_on[i] = 0;
+                        else ++kept;
+                    }
                 }
-                __syncthreads();
-                fbest = bcast[0]; c0c = bcast[1]; c1c = bcast[2];
-                h0 *= 0.32f;
-                h1 *= 0.32f;
                 __syncthreads();
             }
-            if (fbest < fin_f) { fin_f = fbest; fin_p0 = c0c; fin_p1 = c1c; }
+            for (int r = warp; r < K2_NSTART * 8; r += WPS) {
+                const int s = r >> 3, row = r & 7;
+                if (!st_on[s]) continue;
+                if (p.p0_only && row > 0) { if (lane == 0) rf[r] = CUDART_INF_F; continue; }
+                const float c0c = st_p0[s], c1c = st_p1[s];
+                const float p1 = p.p0_only ? 0.f : fminf(fmaxf(c1c + (float(2 * row) - 7.f) * (1.f / 7.f) * h1, -4000.f), 4000.f);
+                const float tpu = p1 * (1.0f / 360.0f);
+                float c0[K2_K], s0[K2_K], p0k[K2_K];
+#pragma unroll
+                for (int k = 0; k < K2_K; ++k) {
+                    // p0 is periodic: candidates leaving the closed box [-180, 180] re-enter on the other side
+                    float q0 = c0c + (float(2 * k) - 7.f) * (1.f / 7.f) * h0;
+                    q0 = q0 > 180.f ? q0 - 360.f : (q0 < -180.f ? q0 + 360.f : q0);
+                    p0k[k] = q0;
+                    sincospif(q0 * (1.0f / 180.0f), &s0[k], &c0[k]);
+                }
+                Acc<float, METHOD, K2_K> acc;
+                acc.init();
+                if constexpr (METHOD == METHOD_ACME) {
+                    if (use_pairs) {
+                        constexpr int PPL = (N / K2_SUB) / 32;
+                        lane_accumulate_pairs<K2_K>(subp, lane * PPL, (lane + 1) * PPL, tpu, u0, duf, c0, s0, acc);
+                    } else {
+                        lane_accumulate_rt<float, METHOD, K2_K>(sp, PADSHIFT, lane * L, (lane + 1) * L, geom, tpu, u0, duf, c0, s0, acc);
+                    }
+                } else {
+                    lane_accumulate_rt<float, METHOD, K2_K>(sp, PADSHIFT, lane * L, (lane + 1) * L, geom, tpu, u0, duf, c0, s0, acc);
+                }
+                acc.warp_reduce();
+                if constexpr (METHOD == METHOD_ACME) {
+                    if (use_pairs) {
+                        float tp = tpu * upiv;
+                        tp -= floorf(tp);
+                        float sn, cs;
+                        sincospif(2.0f * tp, &sn, &cs);
+                        const float wx = Spiv.x * cs - Spiv.y * sn, wy = Spiv.x * sn + Spiv.y * cs;
+#pragma unroll
+                        for (int k = 0; k < K2_K; ++k) {
+                            acc.a[k][0] *= float(K2_SUB);
+                            acc.a[k][1] *= float(K2_SUB);
+                            acc.a[k][2] *= float(K2_SUB);
+                            acc.a[k][3] = fmaxf(acc.a[k][3], wx * c0[k] - wy * s0[k]);
+                        }
+                    }
+                }
+                float rbf = CUDART_INF_F, rb0 = c0c;
+#pragma unroll
+                for (int k = 0; k < K2_K; ++k) {
+                    const float f = acc.score(k, geom);
+                    if (f < rbf) { rbf = f; rb0 = p0k[k]; }
+                }
+                if (lane == 0) { rf[r] = rbf; rp0[r] = rb0; rp1[r] = p1; }
+            }
+            __syncthreads();
+            if (t < K2_NSTART && st_on[t]) {
+                float bf = st_f[t], b0 = st_p0[t], b1 = st_p1[t];
+                for (int row = 0; row < 8; ++row) {
+                    const int r = t * 8 + row;
+                    if (rf[r] < bf) { bf = rf[r]; b0 = rp0[r]; b1 = rp1[r]; }
+                }
+                st_f[t] = bf; st_p0[t] = b0; st_p1[t] = b1;
+            }
+            h0 *= 0.32f;
+            h1 *= 0.32f;
+            __syncthreads();
         }
+        float fin_f = CUDART_INF_F, fin_p0 = 0.f, fin_p1 = 0.f;
+        for (int s = 0; s < K2_NSTART; ++s)
+            if (st_on[s] && st_f[s] < fin_f) { fin_f = st_f[s]; fin_p0 = st_p0[s]; fin_p1 = st_p1[s]; }
 
         // ---- F: apply the phase and store --------------------------------------------------------------------------------
         {
