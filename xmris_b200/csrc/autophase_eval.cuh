@@ -92,6 +92,11 @@ struct Acc {
             // sum g ln g = 0.5 * (ln2 * A1 - A0 * ln2);   H = ln G - (sum g ln g) / G
             const R sglg = R(0.5) * LN2 * (A1 - A0);
             const R H = RealOps<R>::lnr(G) - sglg / G;
+            // The reference divides by the SIGNED max(d) (phasing.py:122): where the whole real part is negative the
+            // objective is negative with a pole at max(d) -> 0- (SURVEY finding 5).  Such upside-down candidates are
+            // rejected: the search minimises over the region max(d) > 0, which is where the reference's optimiser
+            // lands on well-posed data.
+            if (!(a[k][3] > R(0))) return RealOps<R>::inf();
             return (H + R(1000) * a[k][2]) / R(g.n) / a[k][3];
         }
         if (METHOD == METHOD_POSITIVITY) return R(5) * a[k][0] - a[k][1];
