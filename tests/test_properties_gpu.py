@@ -125,3 +125,26 @@ def test_per_voxel_structure_at_scale():
     rot = torch.polar(torch.ones_like(turns), 2 * np.pi * turns).to(torch.complex64)
     resid = (out - spec * rot).abs().pow(2).sum(dim=1).sqrt() / mag.pow(2).sum(dim=1).sqrt()
     assert float(resid.max()) < 2e-5
+
+
+@pytest.mark.parametrize("mode", ["single", "all"])
+def test_host_pipeline_matches_device_chain(mode):
+    """hostpipe.HostChain (pinned host buffers, chunked + pipelined) == the device-resident chain."""
+    import torch
+    from xmris_b200 import chain, hostpipe, pervoxel
+
+    batch, n = (3000, 2048) if mode == "single" else (700, 1024)
+    fid, t = _fids("1H", batch, n, seed=21)
+    h_in = torch.empty((batch, n), dtype=torch.complex64, pin_memory=True)
+    h_in.copy_(fid)
+    outs = [torch.empty((batch, n), dtype=torch.complex64, pin_memory=True) for _ in range(3)]
+    pipe = hostpipe.HostChain(fid.device, batch, n, t, None, "end", 5.0, mode=mode, peak_width=100, chunk=1024)
+    pipe.run(h_in, outs[0])
+    infos = pipe.run_many([(h_in, outs[1]), (h_in, outs[2])])
+    if mode == "single":
+        ref, _, info = chain.chain_single(fid, t, None, "end", 5.0, peak_width=100)
+        assert (infos[0]["p0"], infos[0]["p1"], infos[0]["pivot"]) == (info["p0"], info["p1"], info["pivot"])
+    else:
+        ref = pervoxel.chain_all_device(fid, t, None, "end", 5.0, peak_width=100)["out"]
+    for o in outs:
+        assert torch.equal(o.cuda(), ref)

@@ -218,7 +218,11 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
                 const int oi = __shfl_xor_sync(0xffffffffu, besti, off);
                 amax_combine(best, besti, ov, oi);
             }
-            if (C::T > 32) {
+            if (F && !do_index) {
+                // max-only fast pass: one atomicMax per warp on the per-spectrum slot (zeroed by the launcher) instead of a
+                // block-wide reduction + barrier; non-negative floats order like their bit patterns.
+                if ((t & 31) == 0 && valid) atomicMax(reinterpret_cast<int*>(p.absmax + spec), __float_as_int(sqrtf(best)));
+            } else if (C::T > 32) {
                 constexpr int WPG = C::T / 32;
                 float* rv = red + size_t(g) * 64;
                 int* ri = reinterpret_cast<int*>(rv) + 32;
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
                     for (int w = 1; w < WPG; ++w) amax_combine(best, besti, rv[w], ri[w]);
                 }
             }
-            if (t == 0 && valid) {
+            if (!(F && !do_index) && t == 0 && valid) {
                 p.absmax[spec] = sqrtf(best);
                 if (do_index) p.argmax[spec] = besti;
             }

@@ -55,7 +55,11 @@ cudaError_t XMR_CAT(k1_launch_, XMR_N)(const K1Params& p, bool inverse, int win,
             return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE>(p, max_ctas, st);
         if (st_ && ph && p.absmax == nullptr)
             return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE | K1_FAST_PHASE>(p, max_ctas, st);
-        if (!st_ && stats) return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STATS>(p, max_ctas, st);
+        if (!st_ && stats) {
+            cudaError_t e = cudaMemsetAsync(p.absmax, 0, sizeof(float) * size_t(p.batch), st);   // atomicMax accumulators
+            if (e != cudaSuccess) return e;
+            return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STATS>(p, max_ctas, st);
+        }
     }
     if (win == 1)
         return tma ? launch_one<XMR_N, false, 1, true>(p, max_ctas, st) : launch_one<XMR_N, false, 1, false>(p, max_ctas, st);
