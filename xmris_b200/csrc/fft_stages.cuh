@@ -103,15 +103,19 @@ XMR_HD void stage0_store(int t, float2* slot, float2* v /* [E] */, const float2*
 
 // ---- stage 1 -------------------------------------------------------------------------------------------
 // tw1_base[j][0..1] = W_M^b, W_M^(4b) for this thread's item j (b = (t + T*j) % R2).
-template <class C, bool INVERSE>
-XMR_HD void stage1(int t, const float2* A, float2* B, const float2* tw1_base /* [C1][2] */) {
-    float2 v[C::E];
+// Split in two so that exchange B can reuse the memory of exchange A (large N: one shared buffer per spectrum):
+// the caller puts a block barrier between stage1_load and stage1_store when A and B alias.
+template <class C>
+XMR_HD void stage1_load(int t, const float2* A, float2* v /* [E] */) {
     XMR_UNROLL
     for (int j = 0; j < C::C1; ++j) {
         const int beta = t + C::T * j, b = beta % C::R2, k1 = beta / C::R2;
         XMR_UNROLL
         for (int a = 0; a < C::R1; ++a) v[j * C::R1 + a] = A[k1 * C::M + C::R2 * a + b];
     }
+}
+template <class C, bool INVERSE>
+XMR_HD void stage1_store(int t, float2* B, float2* v /* [E] */, const float2* tw1_base /* [C1][2] */) {
     XMR_UNROLL
     for (int j = 0; j < C::C1; ++j) {
         const int beta = t + C::T * j, b = beta % C::R2, k1 = beta / C::R2;
@@ -125,6 +129,12 @@ XMR_HD void stage1(int t, const float2* A, float2* B, const float2* tw1_base /* 
             B[c * C::PC + b * C::PB + k1] = z;
         }
     }
+}
+template <class C, bool INVERSE>
+XMR_HD void stage1(int t, const float2* A, float2* B, const float2* tw1_base /* [C1][2] */) {
+    float2 v[C::E];
+    stage1_load<C>(t, A, v);
+    stage1_store<C, INVERSE>(t, B, v, tw1_base);
 }
 
 // ---- stage 2 -------------------------------------------------------------------------------------------

@@ -38,11 +38,16 @@ struct K1Params {
     float2 ph_step[16];    // exp(2 pi i * b * R0*R1 * d), d < 16
 };
 
+// N >= 8192: one shared buffer per spectrum serves as TMA landing slot, exchange A and exchange B ("in-place B"), one
+// ring stage, so that two CTAs fit on an SM (2 x 68 KiB) instead of one (196 KiB with separate buffers).
 template <int N>
 struct K1Smem {
     using C = FftCfg<N>;
-    static constexpr size_t RING = size_t(K1_STAGES) * C::SPB * C::N * sizeof(float2);
-    static constexpr size_t B = size_t(C::SPB) * C::SIZE_B * sizeof(float2);
+    static constexpr bool INPLACE_B = (N >= 8192);
+    static constexpr int STAGES = INPLACE_B ? 1 : K1_STAGES;
+    static constexpr size_t SLOT = INPLACE_B ? (C::SIZE_B > C::N ? C::SIZE_B : C::N) : C::N;   // complex elements
+    static constexpr size_t RING = size_t(STAGES) * C::SPB * SLOT * sizeof(float2);
+    static constexpr size_t B = INPLACE_B ? 0 : size_t(C::SPB) * C::SIZE_B * sizeof(float2);
     static constexpr size_t RED = size_t(C::SPB) * 32 * 8;  // per group: up to 32 warps x (float, int)
     static constexpr size_t BAR = 64;
     static constexpr size_t TOTAL = RING + B + RED + BAR;
@@ -54,7 +59,7 @@ constexpr int k1_min_blocks() {
     int by_smem = int((227u * 1024u) / (K1Smem<N>::TOTAL + 1024));
     int by_thr = 2048 / FftCfg<N>::THREADS;
     int m = by_smem < by_thr ? by_smem : by_thr;
-    if (m > 2) m = 2;   // persistent per-thread twiddles want <= 128 registers/thread at 256 threads
+    if (m > 2) m = 2;   // persistent per-thread twiddles / 32 points per thread want <= 128 registers at 256 threads
     return m < 1 ? 1 : m;
 }
 
@@ -76,6 +81,9 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
     constexpr bool F = (FAST != 0);
     constexpr bool TW_PERSIST = (N <= 4096);
     constexpr int NTW = (C::R0 > 1) ? C::C0 * (C::R0 - 1) : 1;
+    constexpr bool IPB = K1Smem<N>::INPLACE_B;
+    constexpr int STAGES = K1Smem<N>::STAGES;
+    constexpr size_t SLOT = K1Smem<N>::SLOT;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2* ring = reinterpret_cast<float2*>(smem_raw);
@@ -128,22 +136,22 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
         const int nvalid = int((p.batch - s0) < C::SPB ? (p.batch - s0) : C::SPB);
         const uint32_t row_bytes = uint32_t(n_in) * 8u;
         mbar_arrive_expect_tx(&bars[slot], row_bytes * nvalid);
-        float2* dst = ring + size_t(slot) * C::SPB * C::N;
-        if (n_in == C::N) {
+        float2* dst = ring + size_t(slot) * C::SPB * SLOT;
+        if (n_in == C::N && SLOT == size_t(C::N)) {
             bulk_g2s(dst, p.in + s0 * n_in, row_bytes * nvalid, &bars[slot]);
         } else {
-            for (int r = 0; r < nvalid; ++r) bulk_g2s(dst + size_t(r) * C::N, p.in + (s0 + r) * n_in, row_bytes, &bars[slot]);
+            for (int r = 0; r < nvalid; ++r) bulk_g2s(dst + size_t(r) * SLOT, p.in + (s0 + r) * n_in, row_bytes, &bars[slot]);
         }
     };
 
     if (TMA) {
         if (tid == 0) {
-            for (int s = 0; s < K1_STAGES; ++s) mbar_init(&bars[s], 1);
+            for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
             fence_mbar_init();
         }
         __syncthreads();
         if (tid == 0) {
-            for (int s = 0; s < K1_STAGES; ++s) {
+            for (int s = 0; s < STAGES; ++s) {
                 const long long tile = blockIdx.x + (long long)s * gridDim.x;
                 if (tile < ntiles) issue(tile, s);
             }
@@ -152,14 +160,14 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
 
     int it = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int slot = it % K1_STAGES;
+        const int slot = it % STAGES;
         const long long spec = tile * C::SPB + g;
         const bool valid = spec < p.batch;
-        float2* my_slot = ring + (size_t(slot) * C::SPB + g) * C::N;
-        float2* my_B = Bbuf + size_t(g) * C::SIZE_B;
+        float2* my_slot = ring + (size_t(slot) * C::SPB + g) * SLOT;
+        float2* my_B = IPB ? my_slot : Bbuf + size_t(g) * C::SIZE_B;
 
         if (TMA) {
-            mbar_wait(&bars[slot], (it / K1_STAGES) & 1);
+            mbar_wait(&bars[slot], (it / STAGES) & 1);
         } else {
             // plain-load path (unaligned base or odd n_in): cooperative coalesced copy of the tile's rows
             const long long s0 = tile * C::SPB;
@@ -167,7 +175,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
             __syncthreads();   // previous tile's readers of this slot are done
             for (int idx = tid; idx < nvalid * n_in; idx += C::THREADS) {
                 const int r = idx / n_in, k = idx - r * n_in;
-                ring[(size_t(slot) * C::SPB + r) * C::N + k] = p.in[(s0 + r) * n_in + k];
+                ring[(size_t(slot) * C::SPB + r) * SLOT + k] = p.in[(s0 + r) * n_in + k];
             }
             __syncthreads();
         }
@@ -179,11 +187,17 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
         stage0_store<C, INVERSE, TW_PERSIST>(t, my_slot, v, tw_persist, tw0_base);
         __syncthreads();
         // ---- stage 1: R1-point DFTs, exchange B ----------------------------------------------------------
-        stage1<C, INVERSE>(t, my_slot, my_B, tw1_base);
+        if (IPB) {
+            stage1_load<C>(t, my_slot, v);
+            __syncthreads();                       // exchange B overwrites exchange A: every thread has its inputs
+            stage1_store<C, INVERSE>(t, my_B, v, tw1_base);
+        } else {
+            stage1<C, INVERSE>(t, my_slot, my_B, tw1_base);
+        }
         __syncthreads();
-        // the input slot is free again: prefetch tile it+STAGES into it while stage 2 and the epilogue run
-        if (TMA && tid == 0) {
-            const long long nt = tile + (long long)K1_STAGES * gridDim.x;
+        // separate buffers: the input slot is free again -> prefetch tile it+STAGES while stage 2 and the epilogue run
+        if (!IPB && TMA && tid == 0) {
+            const long long nt = tile + (long long)STAGES * gridDim.x;
             if (nt < ntiles) {
                 fence_proxy_async_smem();
                 issue(nt, slot);
@@ -191,6 +205,16 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
         }
         // ---- stage 2: R2-point DFTs, results in registers ------------------------------------------------
         stage2<C, INVERSE>(t, my_B, v);
+        if (IPB) {
+            __syncthreads();                       // the shared buffer is free once every thread holds its results
+            if (TMA && tid == 0) {
+                const long long nt = tile + (long long)STAGES * gridDim.x;
+                if (nt < ntiles) {
+                    fence_proxy_async_smem();
+                    issue(nt, slot);
+                }
+            }
+        }
 
         // ---- epilogue --------------------------------------------------------------------------------------
         constexpr int Q = C::R0 * C::R1;
