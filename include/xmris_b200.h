@@ -13,7 +13,8 @@
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream) unless it
  *     says otherwise.  No hidden allocation except a per-(device, N) twiddle-table cache guarded by a mutex.
  *   - return value: 0 on success, else one of XMR_ERR_*; xmr_last_error() returns the thread-local message.
- *   - supported transform lengths n_out: powers of two in [16, 8192] (one spectrum per CTA-resident slot).
+ *   - supported transform lengths n_out: powers of two in [16, 8192] (one spectrum per CTA-resident slot); the Python
+ *     layer composes other lengths (<= 4096) from these entry points as a chirp-z transform.
  */
 #ifndef XMRIS_B200_H
 #define XMRIS_B200_H

@@ -151,3 +151,28 @@ def test_autophase_single_on_batch(xm):
         sp.xmr.autophase(mode="nope")
     with pytest.raises(ValueError, match="Method"):
         sp.xmr.autophase(method="nope")
+
+
+def test_non_power_of_two_chain_like_bruker_example(xm):
+    """1972-point FIDs (the length the reference's Bruker notebook produces after digital-filter removal,
+    docs/notebooks/vendor/bruker_fid_loader.md:93-121): to_spectrum().autophase() through the chirp-z path."""
+    from xmris_b200.synth import make_fids_numpy
+
+    fid, t, _ = make_fids_numpy("1H", 5, 1972, seed=31)
+    da = xm.xr.DataArray(fid, dims=["average", "time"], coords={"time": t}, attrs={"PVM_SpecSWH": 5000.0})
+    sp = da.xmr.to_spectrum()
+    ref_spec, ref_freqs = orc.to_spectrum(fid.astype(np.complex64).astype(np.complex128), 1, t)
+    np.testing.assert_array_equal(sp.coords["frequency"].values, ref_freqs)
+    assert max(rel_l2(sp.values[i], ref_spec[i]) for i in range(5)) < TOL
+    out = sp.xmr.autophase()
+    ref_out, info = orc.autophase(ref_spec, 1, ref_freqs, peak_width=100)
+    assert out.attrs["phase_pivot"] == info["pivot"]
+    f_gpu = orc.acme_score([out.attrs["phase_p0"], out.attrs["phase_p1"]], ref_spec[info["slice"]], ref_freqs, info["pivot"])
+    assert f_gpu <= info["fun"] * (1 + 1e-6)
+    close = abs(out.attrs["phase_p0"] - info["p0"]) < ANG and abs(out.attrs["phase_p1"] - info["p1"]) < ANG
+    assert close or f_gpu < info["fun"]
+    fused = da.xmr.process_fid(autophase_kwargs=dict(peak_width=100))
+    assert abs(fused.attrs["phase_p0"] - out.attrs["phase_p0"]) < 0.05
+    assert max(rel_l2(fused.values[i], out.values[i]) for i in range(5)) < 1e-3
+    back = sp.xmr.to_fid()
+    assert rel_l2(back.values, fid) < TOL

@@ -160,8 +160,29 @@ def test_errors(dev):
     import torch
     from xmris_b200 import device as D
 
-    x = torch.zeros((2, 1972), dtype=torch.complex64, device=dev)
+    x = torch.zeros((2, 5000), dtype=torch.complex64, device=dev)
     with pytest.raises(ValueError, match="not supported"):
         D.fid_to_spectrum(x)
     with pytest.raises(TypeError):
         D.fid_to_spectrum(torch.zeros((2, 64), dtype=torch.complex64))
+
+
+@pytest.mark.parametrize("n_in,n_out", [(1972, 1972), (1000, 1000), (37, 37), (1972, 3000), (100, 1234), (3, 3)])
+def test_arbitrary_length_chirp_z(dev, n_in, n_out):
+    """Lengths that are not powers of two (the 1972-point Bruker FIDs of docs/notebooks/vendor/bruker_fid_loader.md)."""
+    import torch
+    from xmris_b200 import device as D
+
+    rng = np.random.default_rng(n_in + n_out)
+    x = _rand(rng, (7, n_in))
+    t = 2e-4 * np.arange(n_in)
+    ref, freqs = orc.chain_to_spectrum(x.astype(np.complex128), 1, t, n_out if n_out > n_in else None, "end", 3.0)
+    _, t_pad, _ = orc.zero_fill(np.zeros(n_in), 0, t, n_out, "end")
+    w = np.exp(-np.pi * 3.0 * (t_pad if n_out > n_in else t)) / np.sqrt(n_out)
+    spec, amax, imax = D.fid_to_spectrum(torch.from_numpy(x).to(dev), n_out=n_out, window=w, want_stats=True)
+    got = spec.cpu().numpy()
+    assert max(rel_l2(got[i], ref[i]) for i in range(7)) < TOL
+    np.testing.assert_allclose(amax.cpu().numpy(), np.abs(ref).max(axis=1), rtol=3e-5)
+    back, _, _ = D.fid_to_spectrum(spec, inverse=True, in_shift=n_out // 2, out_shift=0)
+    ref_back, _ = orc.to_fid(ref, 1, freqs)
+    assert rel_l2(back.cpu().numpy(), ref_back) < TOL

@@ -57,6 +57,8 @@ def _win(geo, device):
     """The chain's window, uploaded once per (geometry, device)."""
     if geo["window"] is None:
         return None
+    if geo["n_out"] not in D.SUPPORTED_N:
+        return geo["window"]          # chirp-z path takes the float64 window as is
     cache = geo.setdefault("_prepared", {})
     key = (device.type, device.index)
     if key not in cache:

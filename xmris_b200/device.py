@@ -44,12 +44,77 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+BLUESTEIN_MAX_N = 4096  # arbitrary lengths up to here run as a chirp-z transform over a power-of-two length <= 8192
+
+
 def check_length(n_out: int):
-    if n_out not in SUPPORTED_N:
+    if n_out not in SUPPORTED_N and not (2 <= n_out <= BLUESTEIN_MAX_N):
         raise ValueError(
-            f"xmris_b200: transform length {n_out} is not supported (powers of two in [16, 8192]); "
-            "there is no CPU fallback"
+            f"xmris_b200: transform length {n_out} is not supported (powers of two in [16, 8192], or any length up to "
+            f"{BLUESTEIN_MAX_N} through the chirp-z path); there is no CPU fallback"
         )
+
+
+_bluestein_tables = {}
+
+
+def _bluestein_plan(n: int, inverse: bool, device):
+    """Host float64 tables of the chirp-z (Bluestein) transform of length n over M = 2^ceil(log2(2n-1)) points.
+
+    X_k = c_k * sum_j (x_j c_j) conj(c)_(k-j),  c_j = exp(-/+ i pi j^2 / n)   (j^2 reduced mod 2n in integers: exact phase)
+    """
+    key = (n, bool(inverse), device.type, device.index)
+    plan = _bluestein_tables.get(key)
+    if plan is None:
+        torch = _torch()
+        m = 1
+        while m < 2 * n - 1:
+            m *= 2
+        m = max(m, 16)
+        j = np.arange(n, dtype=np.int64)
+        ang = np.pi * ((j * j) % (2 * n)).astype(np.float64) / n
+        chirp = np.exp((1j if inverse else -1j) * ang)               # c_j
+        b = np.zeros(m, dtype=np.complex128)
+        b[:n] = np.conj(chirp)
+        b[m - n + 1:] = np.conj(chirp[1:][::-1])
+        filt = np.fft.fft(b)                                          # applied between the two power-of-two FFTs
+        plan = dict(m=m, chirp=chirp, filt_dev=torch.from_numpy(filt.astype(np.complex64)).to(device))
+        _bluestein_tables[key] = plan
+    return plan
+
+
+def _fft_any_length(fid, n_out, pad_left, window, scale, inverse, in_shift, out_shift, stream=None):
+    """DFT of arbitrary length n_out <= BLUESTEIN_MAX_N (e.g. the 1972-point Bruker FIDs): chirp-z over K1's
+    power-of-two transforms.  Five launches (pre-chirp, FFT_M, filter, IFFT_M, post-chirp); not a fused fast path."""
+    torch = _torch()
+    n_in = fid.shape[-1]
+    batch_shape = tuple(fid.shape[:-1])
+    flat = fid.reshape(-1, n_in)
+    plan = _bluestein_plan(n_out, inverse, fid.device)
+    m, chirp = plan["m"], plan["chirp"]
+    if in_shift:
+        flat = torch.roll(flat, -int(in_shift), dims=1).contiguous()      # x[k] <- fid[(k + in_shift) mod n]
+    w = np.full(n_out, 1.0 if scale is None else float(scale)) if window is None else np.asarray(window, dtype=np.float64)
+    pre = (w * chirp)[pad_left:pad_left + n_in]
+    y = rotate_rows(flat, pre, stream=stream)
+    big, _, _ = fid_to_spectrum(y, n_out=m, pad_left=int(pad_left), scale=1.0, out_shift=0, stream=stream)
+    big = _rotate_rows_dev(big, plan["filt_dev"], stream)
+    conv, _, _ = fid_to_spectrum(big, inverse=True, scale=1.0 / m, in_shift=0, out_shift=0, stream=stream)
+    head = conv[:, :n_out].contiguous()
+    out = rotate_rows(head, chirp, stream=stream)
+    if out_shift:
+        out = torch.roll(out, int(out_shift), dims=1).contiguous()        # bin j -> (j + out_shift) mod n
+    return out.reshape(batch_shape + (n_out,))
+
+
+def _rotate_rows_dev(x, rot_dev, stream=None):
+    torch = _torch()
+    lib = _lib.load()
+    n = x.shape[-1]
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.xmr_rotate_rows_c64(_ptr(x), _ptr(out), x.numel() // max(n, 1), n, _ptr(rot_dev), _stream_ptr(stream)))
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -120,6 +185,24 @@ def fid_to_spectrum(fid, n_out=None, pad_left=0, window=None, scale=None, invers
         out_shift = n_out // 2
     if scale is None:
         scale = 1.0 / math.sqrt(n_out)
+    if n_out not in SUPPORTED_N:
+        # arbitrary length: chirp-z composition of the power-of-two kernels (statistics / phase applied afterwards)
+        if isinstance(window, PreparedWindow):
+            raise ValueError("PreparedWindow is only defined for power-of-two lengths")
+        spec = _fft_any_length(fid, n_out, int(pad_left), window, scale, bool(inverse), int(in_shift), int(out_shift),
+                               stream)
+        if phase_turns is not None:
+            m = np.arange(n_out)
+            spec = rotate_rows(spec, np.exp(2j * np.pi * (float(phase_turns[0]) + float(phase_turns[1]) * m)), stream)
+        absmax = argmax = None
+        if want_stats:
+            absmax, argmax = row_absmax(spec, stream)
+            if not want_index:
+                argmax = None
+        if out is not None and store:
+            out.copy_(spec)
+            spec = out
+        return (spec if store else None), absmax, argmax
     dev = fid.device
     spec = None
     if store:

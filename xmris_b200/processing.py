@@ -216,6 +216,7 @@ def to_fid(da, dim: str = DIMS.frequency, out_dim: str = DIMS.time):
     n = da.sizes[dim]
     freqs = np.asarray(da.coords[dim].values)
     axis = da.get_axis_num(dim)
+    # ifftshift = roll by (n+1)//2 (fourier.py:57-58): x[k] = S[(k - (n+1)//2) mod n] = S[(k + n//2) mod n]
     fid, _, _ = D.fid_to_spectrum(_to_device(da.values, axis), inverse=True, in_shift=n // 2, out_shift=0)
     res = da.copy(data=_from_device(fid, axis))
     if out_dim is not None and out_dim != dim:
