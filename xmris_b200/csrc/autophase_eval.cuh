@@ -34,7 +34,8 @@ template <> struct RealOps<float> {
     static __device__ __forceinline__ float ab(float a) { return fabsf(a); }
     static __device__ __forceinline__ float tiny() { return 1.17549435e-38f; }
     static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
-    static __device__ __forceinline__ float lnr(float x) { return logf(x); }
+    static __device__ __forceinline__ float lnr(float x) { return __logf(x); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
 };
 template <> struct RealOps<double> {
     static __device__ __forceinline__ void sincospi2(double turns, double* s, double* c) { sincospi(2.0 * turns, s, c); }
@@ -45,6 +46,7 @@ template <> struct RealOps<double> {
     static __device__ __forceinline__ double tiny() { return 2.2250738585072014e-308; }
     static __device__ __forceinline__ double inf() { return CUDART_INF; }
     static __device__ __forceinline__ double lnr(double x) { return log(x); }
+    static __device__ __forceinline__ double div(double a, double b) { return a / b; }
 };
 
 struct ScoreGeom {
@@ -91,13 +93,13 @@ struct Acc {
             const R G = R(0.5) * A0;
             // sum g ln g = 0.5 * (ln2 * A1 - A0 * ln2);   H = ln G - (sum g ln g) / G
             const R sglg = R(0.5) * LN2 * (A1 - A0);
-            const R H = RealOps<R>::lnr(G) - sglg / G;
+            const R H = RealOps<R>::lnr(G) - RealOps<R>::div(sglg, G);
             // The reference divides by the SIGNED max(d) (phasing.py:122): where the whole real part is negative the
             // objective is negative with a pole at max(d) -> 0- (SURVEY finding 5).  Such upside-down candidates are
             // rejected: the search minimises over the region max(d) > 0, which is where the reference's optimiser
             // lands on well-posed data.
             if (!(a[k][3] > R(0))) return RealOps<R>::inf();
-            return (H + R(1000) * a[k][2]) / R(g.n) / a[k][3];
+            return RealOps<R>::div(H + R(1000) * a[k][2], R(g.n) * a[k][3]);
         }
         if (METHOD == METHOD_POSITIVITY) return R(5) * a[k][0] - a[k][1];
         const R mina = (g.roi_start < g.target_idx) ? a[k][0] : a[k][2];

@@ -9,7 +9,7 @@
 //   D  coarse grid (p0 step 15 deg x p1 step 45 deg over the reference's box) of the reference's objective, ACME on
 //      the pair subsample (each warp: one p1, eight p0 per walk), local methods on their ROI
 //   E  the NSTART best, mutually separated cells are refined by NROUND rounds of an 8x8 zoom on the FULL
-//      spectrum (each warp one p1 row, eight p0), shrinking the window ~3.1x per round
+//      spectrum (each warp one p1 row, eight p0), shrinking the window ~3.1x per round, pruning starts as it goes
 //   F  out[m] = S[m] * exp(i*(p0 + p1*u_m)) and (p0, p1, pivot, objective) per voxel
 // HBM traffic per voxel is still 8*n_in + 8*n_out (+ 24 B of results); the search makes this kernel SFU/FP32-bound.
 #pragma once
@@ -28,7 +28,10 @@ constexpr int K2_SUB = 4;        // coarse stage: every 4th point pair
 constexpr int K2_K = 8;          // p0 candidates per walk
 constexpr int K2_NP0 = 24;       // coarse p0: -180 + 15*k
 constexpr int K2_NP1 = 179;      // coarse p1: -4000 + 45*k (last clamped to 4000)
-constexpr int K2_NSTART = 6;
+#ifndef XMR_K2_NSTART
+#define XMR_K2_NSTART 4
+#endif
+constexpr int K2_NSTART = XMR_K2_NSTART;
 constexpr int K2_NROUND = 7;
 constexpr int K2_NSHORT = 64;     // coarse cells re-evaluated at the finer subsample
 constexpr int K2_NP0_ONLY = 121; // p0_only coarse: -180 + 3*k
@@ -416,9 +419,10 @@ k2_kernel(const __grid_constant__ K2Params p) {
 
         // Zoom refinement with successive pruning.  Every round evaluates, for each active start, an 8x8 window
         // (8 p1 rows x 8 p0) around its current centre; rows of all active starts are spread over the warps.
-        //   rounds 0-1: all NSTART starts        (window +-15 x +-45 deg -> +-1.5 x +-4.6 deg)
-        //   rounds 2-3: the best 3 distinct starts
-        //   rounds 4-6: the best 2                (final spacing 0.005 x 0.014 deg)
+        //   rounds 0-1: all NSTART (4) starts     (window +-15 x +-45 deg -> +-1.5 x +-4.6 deg)
+        //   rounds 2-3: the best 2 distinct starts
+        //   rounds 4-6: the best one              (final spacing 0.005 x 0.014 deg)
+        // (tools/validate_pervoxel.py: 6/3/2 starts give the same quality within noise at 1.3x the cost)
         // All rounds use the FULL spectrum: the pair subsample only localises basins -- its noise-induced fine structure
         // (local minima every ~25 deg of p1) differs from the full objective's, so it must not steer the refinement.
         if (t < K2_NSTART) {
@@ -434,7 +438,13 @@ k2_kernel(const __grid_constant__ K2Params p) {
             if (round == 2 || round == 4) {
                 // prune: keep the best `keep` starts that are not duplicates of a better one
                 if (t == 0) {
-                    const int keep = (round == 2) ? 3 : 2;
+#ifndef XMR_K2_KEEP_A
+#define XMR_K2_KEEP_A 2
+#endif
+#ifndef XMR_K2_KEEP_B
+#define XMR_K2_KEEP_B 1
+#endif
+                    const int keep = (round == 2) ? XMR_K2_KEEP_A : XMR_K2_KEEP_B;
                     int kept = 0;
                     bool used[K2_NSTART];
                     for (int i = 0; i < K2_NSTART; ++i) used[i] = false;
