@@ -48,8 +48,8 @@ def launches(src, dst):
         f.write("| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
         for k, (c, v) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k}` | {c} | {v/1e6:.3f} | {100*v/total:.1f} % |\n")
-        f.write("\nLast 12 launches (one chain step):\n\n| # | kernel | µs |\n|---|---|---:|\n")
-        for i, (n, v) in enumerate(mine[-12:]):
+        f.write("\nLast 13 launches (one chain step):\n\n| # | kernel | µs |\n|---|---|---:|\n")
+        for i, (n, v) in enumerate(mine[-13:]):
             f.write(f"| {i} | `{n.split('(')[0][:90]}` | {v/1e3:.1f} |\n")
 
 
