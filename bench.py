@@ -335,6 +335,21 @@ def run_ours(args):
                "d2h_bytes_per_step": int(eb * n * 8), "voxels_per_gpu": eb, "ms_per_step": dt * 1e3,
                "api": "hostpipe.HostChain.run_many: pinned host batches, H2D of batch i+1 overlaps D2H of batch i"}
 
+        # the same chain through ONE C-ABI call on the same pinned host buffers (numpy view, no torch on the path)
+        if dist is None:
+            from xmris_b200 import hostabi
+
+            np_in, np_out = h_in.numpy(), h_out.numpy()
+            ap = dict(mode=args.mode, peak_width=PEAK_WIDTH)
+            hostabi.chain_host(np_in, t, None, "end", LB, autophase=ap, out=np_out)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                hostabi.chain_host(np_in, t, None, "end", LB, autophase=ap, out=np_out)
+            dtc = (time.perf_counter() - t0) / 3
+            e2e["c_abi_single_call"] = {"value": eb / dtc, "unit": "spectra/s", "ms_per_call": dtc * 1e3,
+                                        "api": "xmr_chain_host_c64 (one synchronous call per batch, no overlap across batches)"}
+            hostabi.release_workspace()
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

@@ -119,6 +119,35 @@ int xmr_chain_each_c64(const void* in_dev, void* out_dev, int64_t batch, int n_i
                        int index_width, int p0_only, double* p0_dev, double* p1_dev, int* pivot_dev, float* fun_dev,
                        void* stream);
 
+/* The whole chain on HOST buffers in one synchronous call (numpy-side bindings need nothing but ctypes):
+ *   fid_host [batch, n_in] complex64  ->  out_host [batch, n_out] complex64
+ *   zero_fill -> apodize (window_host) -> to_spectrum [-> autophase]           (README.md:66-73 of the reference)
+ * Uploads, kernels and downloads are pipelined over voxel chunks on internal streams; pageable buffers are page-locked
+ * for the duration of the call.  Device scratch is a per-thread workspace (xmr_host_workspace_release() frees it).
+ *   autophase_mode 0: none; 1: the reference's mode="single" (two passes over the device-resident FIDs);
+ *                  2: per spectrum (mode="all", one pass).
+ *   result_host    mode 1: double[4] = {p0 deg, p1 deg, index of the pivot (global |S| maximum) on the output axis, objective}
+ *   p0_host .. fun_host  mode 2: per-voxel results [batch] (fun_host may be NULL)
+ */
+typedef struct xmr_host_chain_desc {
+    int n_in, n_out, pad_left;
+    const double* window_host; /* n_out weights incl. 1/sqrt(n_out) (fid.py:136 with the ortho norm), or NULL          */
+    float scale;               /* used when window_host is NULL; 0 -> 1/sqrt(n_out)                                     */
+    int autophase_mode;
+    int method;                /* XMR_METHOD_*                                                                          */
+    int index_width;           /* ROI half width in points (phasing.py:245-247)                                         */
+    int p0_only;
+    int fixed_pivot;           /* target_coord given: u0_fixed / fixed_target apply to every spectrum                   */
+    double u0_fixed;
+    int fixed_target;
+    double du;                 /* (x[1]-x[0]) / (x_max - x_min) of the output axis (phasing.py:56-69)                   */
+    int chunk;                 /* spectra per pipeline chunk; 0 -> 8192                                                 */
+} xmr_host_chain_desc;
+
+int xmr_chain_host_c64(const xmr_host_chain_desc* desc, const void* fid_host, void* out_host, int64_t batch,
+                       double* result_host, double* p0_host, double* p1_host, int* pivot_host, float* fun_host);
+int xmr_host_workspace_release(void);
+
 #ifdef __cplusplus
 }
 #endif

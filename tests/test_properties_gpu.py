@@ -148,3 +148,30 @@ def test_host_pipeline_matches_device_chain(mode):
         ref = pervoxel.chain_all_device(fid, t, None, "end", 5.0, peak_width=100)["out"]
     for o in outs:
         assert torch.equal(o.cuda(), ref)
+
+
+@pytest.mark.parametrize("mode,n_in,zf", [(None, 2048, None), ("single", 1024, 2048), ("single", 4096, None), ("all", 1024, None)])
+def test_host_c_abi_chain_matches_device_chain(mode, n_in, zf):
+    """xmr_chain_host_c64 (numpy in, numpy out, pageable memory, no torch) == the device-resident chain."""
+    import torch
+    from xmris_b200 import chain, hostabi, pervoxel
+
+    batch = 2500
+    fid, t = _fids("1H", batch, n_in, seed=33)
+    host = fid.cpu().numpy()
+    ap = None if mode is None else dict(mode=mode, peak_width=100)
+    out, freqs, info = hostabi.chain_host(host.reshape(50, 50, n_in), t, zf, "end", 5.0, autophase=ap, chunk=700)
+    assert out.shape == (50, 50, zf or n_in)
+    if mode is None:
+        ref, rfreqs, _ = chain.chain_to_spectrum(fid, t, zf, "end", 5.0)
+    elif mode == "single":
+        ref, rfreqs, rinfo = chain.chain_single(fid, t, zf, "end", 5.0, peak_width=100)
+        assert (info["p0"], info["p1"], info["pivot"]) == (rinfo["p0"], rinfo["p1"], rinfo["pivot"])
+    else:
+        r = pervoxel.chain_all_device(fid, t, zf, "end", 5.0, peak_width=100)
+        ref, rfreqs = r["out"], r["freqs"]
+        np.testing.assert_array_equal(info["p0"].ravel(), r["p0"].cpu().numpy())
+        np.testing.assert_array_equal(info["p1"].ravel(), r["p1"].cpu().numpy())
+    np.testing.assert_array_equal(freqs, rfreqs)
+    assert np.array_equal(out.reshape(batch, -1), ref.cpu().numpy())
+    hostabi.release_workspace()

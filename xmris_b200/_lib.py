@@ -45,7 +45,19 @@ SIGNATURES = {
     "xmr_autophase_search_c64": (_i, [_vp, _i, _d, _d, _i, _i, _i, _i, _vp, _vp, _vp]),
     "xmr_chain_each_c64": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp, _f, _i, _d, _i, _d, _i, _i, _i,
                                 _vp, _vp, _vp, _vp, _vp]),
+
+    "xmr_chain_host_c64": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "xmr_host_workspace_release": (_i, []),
 }
+
+
+class HostChainDesc(ctypes.Structure):
+    """``xmr_host_chain_desc`` of include/xmris_b200.h."""
+
+    _fields_ = [("n_in", _i), ("n_out", _i), ("pad_left", _i), ("window_host", _vp), ("scale", _f),
+                ("autophase_mode", _i), ("method", _i), ("index_width", _i), ("p0_only", _i), ("fixed_pivot", _i),
+                ("u0_fixed", _d), ("fixed_target", _i), ("du", _d), ("chunk", _i)]
+
 
 _lib = None
 

@@ -151,7 +151,7 @@ def run_chain_dataarray(da, dim, out_dim, target_points, position, lb, autophase
     axis = da.get_axis_num(dim)
     n_in = da.sizes[dim]
     t = np.asarray(da.coords[dim].values, dtype=np.float64)
-    fid_t = P._to_device(da.values, axis)
+    fid_t = None
     attrs = dict(da.attrs)
     name = da.name
     padded = target_points is not None and target_points > n_in
@@ -163,10 +163,23 @@ def run_chain_dataarray(da, dim, out_dim, target_points, position, lb, autophase
         if name != dim:
             name = None
     target = out_dim if out_dim is not None else dim
-    if autophase_kwargs is None:
+    n_out_chk = int(target_points) if padded else n_in
+    use_host_abi = n_out_chk in D.SUPPORTED_N and (autophase_kwargs is None or (
+        autophase_kwargs.get("lb", 0.0) == 0.0 and (autophase_kwargs.get("mode", "single") != "all" or n_out_chk >= 512)))
+    if use_host_abi:
+        # numpy in -> ONE C-ABI call on host buffers -> numpy out (no torch on this path)
+        from . import hostabi
+
+        moved = np.ascontiguousarray(np.moveaxis(np.asarray(da.values), axis, -1), dtype=np.complex64)
+        out_np, freqs, info = hostabi.chain_host(moved, t, target_points if padded else None, position, lb,
+                                                 autophase=autophase_kwargs)
+        spec = None
+    elif autophase_kwargs is None:
+        fid_t = P._to_device(da.values, axis)
         spec, freqs, _ = chain_to_spectrum(fid_t, t, target_points if padded else None, position, lb)
         info = None
     else:
+        fid_t = P._to_device(da.values, axis)
         kw = dict(autophase_kwargs)
         mode = kw.pop("mode", "single")
         if mode == "all":
@@ -186,7 +199,11 @@ def run_chain_dataarray(da, dim, out_dim, target_points, position, lb, autophase
     coords = {k: da.coords[k] for k in da.coords if dim not in da.coords[k].dims}
     _, var = P._spectrum_coord(dim, out_dim, freqs)
     coords[target] = var
-    res = xr.DataArray(P._from_device(spec, axis), dims=dims, coords=coords, attrs=attrs, name=name)
+    if spec is None:
+        values = np.ascontiguousarray(np.moveaxis(out_np, -1, axis)).astype(P.OUTPUT_DTYPE, copy=False)
+    else:
+        values = P._from_device(spec, axis)
+    res = xr.DataArray(values, dims=dims, coords=coords, attrs=attrs, name=name)
     if info is not None and np.ndim(info["p0"]) == 0:
         if name != target:
             res.name = None

@@ -1,0 +1,325 @@
+// C ABI: the whole chain on HOST buffers in one call -- what a numpy-side binding of the reference would use.
+//
+//   xmr_chain_host_c64: pinned or pageable host FIDs -> (H2D || pass 1) -> argmax + search -> (pass 2 || D2H) -> host spectra
+//
+// Copies and kernels are pipelined over voxel chunks on three internal streams (created once per thread); device
+// scratch is a per-thread workspace that grows on demand and is released by xmr_host_workspace_release().
+// Pageable buffers are page-locked for the duration of the call (cudaHostRegister) so that the copies are truly
+// asynchronous; already pinned buffers are used as they are.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/xmris_b200.h"
+#include "abi_common.h"
+
+namespace {
+
+struct Workspace {
+    cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+    void* d_in = nullptr;
+    size_t d_in_bytes = 0;
+    void* d_out[2] = {nullptr, nullptr};
+    size_t d_out_bytes = 0;
+    void* d_small = nullptr;   // absmax / argmax / per-voxel results / window / search result + workspace
+    size_t d_small_bytes = 0;
+    int device = -1;
+};
+thread_local Workspace g_ws;
+
+#define XMR_CU(call)                                                   \
+    do {                                                               \
+        cudaError_t e_ = (call);                                       \
+        if (e_ != cudaSuccess) return xmr_abi::cuda_fail(e_, #call);   \
+    } while (0)
+
+int grow(void** p, size_t* have, size_t need) {
+    if (*have >= need) return XMR_OK;
+    if (*p) XMR_CU(cudaFree(*p));
+    *p = nullptr;
+    *have = 0;
+    XMR_CU(cudaMalloc(p, need));
+    *have = need;
+    return XMR_OK;
+}
+
+int ensure_workspace(size_t in_bytes, size_t out_chunk_bytes, size_t small_bytes) {
+    int dev = 0;
+    XMR_CU(cudaGetDevice(&dev));
+    Workspace& w = g_ws;
+    if (w.device != dev) {
+        if (w.device >= 0) return xmr_abi::fail(XMR_ERR_BAD_ARG, "host workspace belongs to device %d; call xmr_host_workspace_release() first", w.device);
+        XMR_CU(cudaStreamCreateWithFlags(&w.s_in, cudaStreamNonBlocking));
+        XMR_CU(cudaStreamCreateWithFlags(&w.s_cmp, cudaStreamNonBlocking));
+        XMR_CU(cudaStreamCreateWithFlags(&w.s_out, cudaStreamNonBlocking));
+        w.device = dev;
+    }
+    int rc = grow(&w.d_in, &w.d_in_bytes, in_bytes);
+    if (rc != XMR_OK) return rc;
+    if (w.d_out_bytes < out_chunk_bytes) {
+        for (int i = 0; i < 2; ++i) {
+            if (w.d_out[i]) XMR_CU(cudaFree(w.d_out[i]));
+            w.d_out[i] = nullptr;
+        }
+        w.d_out_bytes = 0;
+        for (int i = 0; i < 2; ++i) XMR_CU(cudaMalloc(&w.d_out[i], out_chunk_bytes));
+        w.d_out_bytes = out_chunk_bytes;
+    }
+    return grow(&w.d_small, &w.d_small_bytes, small_bytes);
+}
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+struct HostPin {   // page-lock a pageable range for the duration of the call
+    void* p = nullptr;
+    bool registered = false;
+    int lock(const void* ptr, size_t bytes) {
+        if (bytes == 0 || is_pinned(ptr)) return XMR_OK;
+        cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterDefault);
+        if (e != cudaSuccess) {
+            cudaGetLastError();   // fall back to staged (synchronous) copies: still correct
+            return XMR_OK;
+        }
+        p = const_cast<void*>(ptr);
+        registered = true;
+        return XMR_OK;
+    }
+    ~HostPin() {
+        if (registered) cudaHostUnregister(p);
+    }
+};
+
+// factor w[M*n1 + n2] = cols[n2] * rows[n1] when the window allows it (exponential on a uniform axis)
+bool split_window(const double* w, int n, std::vector<float>& cols, std::vector<float>& rows) {
+    const int m = n < 256 ? n : 256, r0 = n / m;
+    cols.resize(m);
+    rows.assign(32, 1.0f);
+    if (r0 == 1) {
+        for (int i = 0; i < m; ++i) cols[i] = float(w[i]);
+        return true;
+    }
+    if (w[0] == 0.0 || !std::isfinite(w[0])) return false;
+    for (int n1 = 0; n1 < r0; ++n1) {
+        const double r = w[size_t(n1) * m] / w[0];
+        for (int n2 = 0; n2 < m; ++n2) {
+            const double want = w[size_t(n1) * m + n2], got = r * w[n2];
+            if (!(std::fabs(want - got) <= 1e-9 * std::fabs(want) + 1e-300)) return false;
+        }
+        rows[n1] = float(r);
+    }
+    for (int i = 0; i < m; ++i) cols[i] = float(w[i]);
+    return true;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+extern "C" {
+
+int xmr_host_workspace_release(void) {
+    Workspace& w = g_ws;
+    if (w.device < 0) return XMR_OK;
+    cudaDeviceSynchronize();
+    if (w.d_in) cudaFree(w.d_in);
+    for (int i = 0; i < 2; ++i)
+        if (w.d_out[i]) cudaFree(w.d_out[i]);
+    if (w.d_small) cudaFree(w.d_small);
+    if (w.s_in) cudaStreamDestroy(w.s_in);
+    if (w.s_cmp) cudaStreamDestroy(w.s_cmp);
+    if (w.s_out) cudaStreamDestroy(w.s_out);
+    w = Workspace();
+    return XMR_OK;
+}
+
+int xmr_chain_host_c64(const xmr_host_chain_desc* d, const void* fid_host, void* out_host, int64_t batch,
+                       double* result_host, double* p0_host, double* p1_host, int* pivot_host, float* fun_host) {
+    if (!d) return xmr_abi::fail(XMR_ERR_BAD_ARG, "descriptor is NULL");
+    const int n_in = d->n_in, n_out = d->n_out;
+    if (batch < 0 || n_in < 1 || n_out < n_in || d->pad_left < 0 || d->pad_left + n_in > n_out)
+        return xmr_abi::fail(XMR_ERR_BAD_ARG, "bad sizes: batch=%lld n_in=%d n_out=%d pad_left=%d", (long long)batch, n_in, n_out, d->pad_left);
+    if (!(n_out >= 16 && n_out <= 8192 && (n_out & (n_out - 1)) == 0))
+        return xmr_abi::fail(XMR_ERR_UNSUPPORTED_N, "n_out=%d: the host chain needs a power-of-two length in [16, 8192]", n_out);
+    if (d->autophase_mode < 0 || d->autophase_mode > 2) return xmr_abi::fail(XMR_ERR_BAD_ARG, "autophase_mode=%d", d->autophase_mode);
+    if (d->autophase_mode == 2 && n_out < 512) return xmr_abi::fail(XMR_ERR_UNSUPPORTED_N, "per-spectrum autophase needs n_out >= 512");
+    if (batch == 0) return XMR_OK;
+    if (!fid_host || !out_host) return xmr_abi::fail(XMR_ERR_BAD_ARG, "NULL host buffer");
+    if (d->autophase_mode == 1 && !result_host) return xmr_abi::fail(XMR_ERR_BAD_ARG, "result_host is NULL");
+    if (d->autophase_mode == 2 && (!p0_host || !p1_host || !pivot_host))
+        return xmr_abi::fail(XMR_ERR_BAD_ARG, "per-spectrum outputs are NULL");
+
+    const int64_t chunk = std::min<int64_t>(batch, d->chunk > 0 ? d->chunk : 8192);
+    const size_t row_in = size_t(n_in) * 8, row_out = size_t(n_out) * 8;
+    // small device area: absmax[batch] | p0[batch] p1[batch] (double) | pivot[batch] fun[batch] | window | result | search ws
+    const size_t o_absmax = 0;
+    const size_t o_p0 = align_up(o_absmax + size_t(batch) * 4, 256);
+    const size_t o_p1 = o_p0 + size_t(batch) * 8;
+    const size_t o_piv = o_p1 + size_t(batch) * 8;
+    const size_t o_fun = o_piv + size_t(batch) * 4;
+    const size_t o_win = align_up(o_fun + size_t(batch) * 4, 256);
+    const size_t o_res = align_up(o_win + size_t(n_out) * 4, 256);
+    const size_t o_arg = o_res + 64;
+    const size_t o_row = align_up(o_arg + 64, 256);                       // one spectrum + its stats
+    const size_t o_sws = align_up(o_row + row_out + 64, 256);
+    const size_t small = o_sws + size_t(xmr_autophase_workspace_bytes());
+    const bool keep_all_in = (d->autophase_mode == 1);                     // the FIDs are read twice
+    int rc = ensure_workspace(keep_all_in ? size_t(batch) * row_in : 2 * size_t(chunk) * row_in, size_t(chunk) * row_out, small);
+    if (rc != XMR_OK) return rc;
+    Workspace& w = g_ws;
+    unsigned char* sm = static_cast<unsigned char*>(w.d_small);
+    float* absmax = reinterpret_cast<float*>(sm + o_absmax);
+
+    HostPin pin_in, pin_out;
+    pin_in.lock(fid_host, size_t(batch) * row_in);
+    pin_out.lock(out_host, size_t(batch) * row_out);
+
+    // window
+    int win_mode = XMR_WIN_NONE;
+    float* win_dev = nullptr;
+    std::vector<float> cols, rows(32, 1.0f), table;
+    if (d->window_host) {
+        win_dev = reinterpret_cast<float*>(sm + o_win);
+        if (split_window(d->window_host, n_out, cols, rows)) {
+            win_mode = XMR_WIN_SEPARABLE;
+            XMR_CU(cudaMemcpyAsync(win_dev, cols.data(), cols.size() * 4, cudaMemcpyHostToDevice, w.s_cmp));
+        } else {
+            win_mode = XMR_WIN_TABLE;
+            table.resize(n_out);
+            for (int i = 0; i < n_out; ++i) table[i] = float(d->window_host[i]);
+            XMR_CU(cudaMemcpyAsync(win_dev, table.data(), table.size() * 4, cudaMemcpyHostToDevice, w.s_cmp));
+        }
+        XMR_CU(cudaStreamSynchronize(w.s_cmp));   // cols/table are stack-lifetime host vectors
+    }
+    const float scale = d->scale != 0.f ? d->scale : 1.0f / std::sqrt(float(n_out));
+    const int64_t nchunks = (batch + chunk - 1) / chunk;
+    std::vector<cudaEvent_t> in_done(nchunks);
+    for (auto& e : in_done) XMR_CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaEvent_t out_free[2] = {nullptr, nullptr}, cmp_done[2] = {nullptr, nullptr}, in_free[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; ++i) {
+        XMR_CU(cudaEventCreateWithFlags(&out_free[i], cudaEventDisableTiming));
+        XMR_CU(cudaEventCreateWithFlags(&cmp_done[i], cudaEventDisableTiming));
+        XMR_CU(cudaEventCreateWithFlags(&in_free[i], cudaEventDisableTiming));
+    }
+    auto cleanup = [&]() {
+        for (auto& e : in_done) cudaEventDestroy(e);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(out_free[i]); cudaEventDestroy(cmp_done[i]); cudaEventDestroy(in_free[i]); }
+    };
+    const unsigned char* h_in = static_cast<const unsigned char*>(fid_host);
+    unsigned char* h_out = static_cast<unsigned char*>(out_host);
+    unsigned char* d_in = static_cast<unsigned char*>(w.d_in);
+    auto d_in_chunk = [&](int64_t c) { return keep_all_in ? d_in + size_t(c) * chunk * row_in : d_in + size_t(c % 2) * chunk * row_in; };
+
+#define XMR_RC(call)            \
+    do {                        \
+        rc = (call);            \
+        if (rc != XMR_OK) {     \
+            cudaDeviceSynchronize(); \
+            cleanup();          \
+            return rc;          \
+        }                       \
+    } while (0)
+#define XMR_CUC(call)                                      \
+    do {                                                   \
+        cudaError_t e_ = (call);                           \
+        if (e_ != cudaSuccess) {                           \
+            cudaDeviceSynchronize();                       \
+            cleanup();                                     \
+            return xmr_abi::cuda_fail(e_, #call);          \
+        }                                                  \
+    } while (0)
+
+    double ph_a = 0.0, ph_b = 0.0;
+    if (d->autophase_mode == 1) {
+        // ---- pass 1 trails the uploads chunk by chunk ---------------------------------------------------------------
+        for (int64_t c = 0; c < nchunks; ++c) {
+            const int64_t lo = c * chunk, nb = std::min(chunk, batch - lo);
+            XMR_CUC(cudaMemcpyAsync(d_in_chunk(c), h_in + size_t(lo) * row_in, size_t(nb) * row_in, cudaMemcpyHostToDevice, w.s_in));
+            XMR_CUC(cudaEventRecord(in_done[c], w.s_in));
+            XMR_CUC(cudaStreamWaitEvent(w.s_cmp, in_done[c], 0));
+            XMR_RC(xmr_fid_to_spectrum_c64(d_in_chunk(c), nullptr, nb, n_in, n_out, d->pad_left, win_mode, win_dev, rows.data(), scale, 0,
+                                           0, n_out / 2, absmax + lo, nullptr, XMR_PHASE_NONE, 0.0, 0.0, w.s_cmp));
+        }
+        // ---- winner, its spectrum, the search ------------------------------------------------------------------------
+        unsigned char* arg = sm + o_arg;
+        XMR_RC(xmr_global_argmax(absmax, nullptr, batch, n_out, arg, w.s_cmp));
+        unsigned char arg_h[16];
+        XMR_CUC(cudaMemcpyAsync(arg_h, arg, 16, cudaMemcpyDeviceToHost, w.s_cmp));
+        XMR_CUC(cudaStreamSynchronize(w.s_cmp));
+        long long flat;
+        std::memcpy(&flat, arg_h + 8, 8);
+        const long long row = flat / n_out;
+        unsigned char* rowbuf = sm + o_row;
+        float* row_abs = reinterpret_cast<float*>(rowbuf + row_out);
+        int* row_arg = reinterpret_cast<int*>(rowbuf + row_out + 16);
+        XMR_RC(xmr_fid_to_spectrum_c64(d_in + size_t(row) * row_in, rowbuf, 1, n_in, n_out, d->pad_left, win_mode, win_dev, rows.data(),
+                                       scale, 0, 0, n_out / 2, row_abs, row_arg, XMR_PHASE_NONE, 0.0, 0.0, w.s_cmp));
+        int idx = 0;
+        XMR_CUC(cudaMemcpyAsync(&idx, row_arg, 4, cudaMemcpyDeviceToHost, w.s_cmp));
+        XMR_CUC(cudaStreamSynchronize(w.s_cmp));
+        const int target = d->fixed_pivot ? d->fixed_target : idx;
+        const double u0 = d->fixed_pivot ? d->u0_fixed : -d->du * double(idx);
+        double* res = reinterpret_cast<double*>(sm + o_res);
+        XMR_RC(xmr_autophase_search_c64(rowbuf, n_out, u0, d->du, d->method, target, d->index_width > 0 ? d->index_width : 1, d->p0_only,
+                                        res, sm + o_sws, w.s_cmp));
+        double res_h[4];
+        XMR_CUC(cudaMemcpyAsync(res_h, res, 32, cudaMemcpyDeviceToHost, w.s_cmp));
+        XMR_CUC(cudaStreamSynchronize(w.s_cmp));
+        const double p0 = res_h[0], p1 = d->p0_only ? 0.0 : res_h[1];
+        result_host[0] = p0;
+        result_host[1] = p1;
+        result_host[2] = double(idx);
+        result_host[3] = res_h[2];
+        ph_a = p0 / 360.0 + (p1 / 360.0) * u0;
+        ph_b = (p1 / 360.0) * d->du;
+    }
+    // ---- output pass per chunk with the write-back trailing it ----------------------------------------------------------
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int64_t lo = c * chunk, nb = std::min(chunk, batch - lo);
+        const int k = int(c % 2);
+        if (!keep_all_in) {
+            if (c >= 2) XMR_CUC(cudaStreamWaitEvent(w.s_in, in_free[k], 0));   // input slot k was last read by chunk c-2
+            XMR_CUC(cudaMemcpyAsync(d_in_chunk(c), h_in + size_t(lo) * row_in, size_t(nb) * row_in, cudaMemcpyHostToDevice, w.s_in));
+            XMR_CUC(cudaEventRecord(in_done[c], w.s_in));
+        }
+        XMR_CUC(cudaStreamWaitEvent(w.s_cmp, in_done[c], 0));
+        if (c >= 2) XMR_CUC(cudaStreamWaitEvent(w.s_cmp, out_free[k], 0));
+        if (d->autophase_mode == 2) {
+            XMR_RC(xmr_chain_each_c64(d_in_chunk(c), w.d_out[k], nb, n_in, n_out, d->pad_left, 0, win_mode, win_dev, rows.data(), scale,
+                                      d->method, d->du, d->fixed_pivot, d->u0_fixed, d->fixed_target, d->index_width > 0 ? d->index_width : 1,
+                                      d->p0_only, reinterpret_cast<double*>(sm + o_p0) + lo, reinterpret_cast<double*>(sm + o_p1) + lo,
+                                      reinterpret_cast<int*>(sm + o_piv) + lo, reinterpret_cast<float*>(sm + o_fun) + lo, w.s_cmp));
+        } else {
+            XMR_RC(xmr_fid_to_spectrum_c64(d_in_chunk(c), w.d_out[k], nb, n_in, n_out, d->pad_left, win_mode, win_dev, rows.data(), scale, 0, 0,
+                                           n_out / 2, nullptr, nullptr, d->autophase_mode == 1 ? XMR_PHASE_UNIFORM : XMR_PHASE_NONE, ph_a, ph_b,
+                                           w.s_cmp));
+        }
+        XMR_CUC(cudaEventRecord(cmp_done[k], w.s_cmp));
+        if (!keep_all_in) XMR_CUC(cudaEventRecord(in_free[k], w.s_cmp));
+        XMR_CUC(cudaStreamWaitEvent(w.s_out, cmp_done[k], 0));
+        XMR_CUC(cudaMemcpyAsync(h_out + size_t(lo) * row_out, w.d_out[k], size_t(nb) * row_out, cudaMemcpyDeviceToHost, w.s_out));
+        XMR_CUC(cudaEventRecord(out_free[k], w.s_out));
+    }
+    if (d->autophase_mode == 2) {
+        XMR_CUC(cudaMemcpyAsync(p0_host, sm + o_p0, size_t(batch) * 8, cudaMemcpyDeviceToHost, w.s_cmp));
+        XMR_CUC(cudaMemcpyAsync(p1_host, sm + o_p1, size_t(batch) * 8, cudaMemcpyDeviceToHost, w.s_cmp));
+        XMR_CUC(cudaMemcpyAsync(pivot_host, sm + o_piv, size_t(batch) * 4, cudaMemcpyDeviceToHost, w.s_cmp));
+        if (fun_host) XMR_CUC(cudaMemcpyAsync(fun_host, sm + o_fun, size_t(batch) * 4, cudaMemcpyDeviceToHost, w.s_cmp));
+    }
+    XMR_CUC(cudaStreamSynchronize(w.s_cmp));
+    XMR_CUC(cudaStreamSynchronize(w.s_out));
+    XMR_CUC(cudaStreamSynchronize(w.s_in));
+    cleanup();
+    return XMR_OK;
+#undef XMR_RC
+#undef XMR_CUC
+}
+
+}  // extern "C"
