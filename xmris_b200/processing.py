@@ -202,8 +202,17 @@ def to_spectrum(da, dim: str = DIMS.time, out_dim: str = DIMS.frequency):
     n = da.sizes[dim]
     freqs = _fft_freqs(n, da.coords[dim].values)
     axis = da.get_axis_num(dim)
-    spec, _, _ = D.fid_to_spectrum(_to_device(da.values, axis))
-    res = da.copy(data=_from_device(spec, axis))
+    if n in D.SUPPORTED_N:
+        # numpy in -> one C-ABI call on host buffers -> numpy out (xmr_chain_host_c64, no torch on this path)
+        from . import hostabi
+
+        moved = np.ascontiguousarray(np.moveaxis(np.asarray(da.values), axis, -1), dtype=np.complex64)
+        out_np, _, _ = hostabi.chain_host(moved, da.coords[dim].values)
+        values = np.ascontiguousarray(np.moveaxis(out_np, -1, axis)).astype(OUTPUT_DTYPE, copy=False)
+    else:
+        spec, _, _ = D.fid_to_spectrum(_to_device(da.values, axis))    # chirp-z composition for other lengths
+        values = _from_device(spec, axis)
+    res = da.copy(data=values)
     target, var = _spectrum_coord(dim, out_dim, freqs)
     if out_dim is not None and out_dim != dim:
         res = res.rename({dim: out_dim})
