@@ -114,27 +114,30 @@ XMR_HD void stage1_load(int t, const float2* A, float2* v /* [E] */) {
         for (int a = 0; a < C::R1; ++a) v[j * C::R1 + a] = A[k1 * C::M + C::R2 * a + b];
     }
 }
-template <class C, bool INVERSE>
-XMR_HD void stage1_store(int t, float2* B, float2* v /* [E] */, const float2* tw1_base /* [C1][2] */) {
+// tw1_tab (optional, shared memory): W_M^(b*c) at [(c-1)*R2 + b] -- 15 conflict-free 8-byte loads per butterfly instead of
+// a 14-multiply power chain (the FFT is issue-bound, the LSU has headroom).  nullptr: powers of tw1_base.
+template <class C, bool INVERSE, bool TAB = false>
+XMR_HD void stage1_store(int t, float2* B, float2* v /* [E] */, const float2* tw1_base /* [C1][2] */,
+                         const float2* tw1_tab = nullptr) {
     XMR_UNROLL
     for (int j = 0; j < C::C1; ++j) {
         const int beta = t + C::T * j, b = beta % C::R2, k1 = beta / C::R2;
         dft_dif<C::R1, INVERSE>(v + j * C::R1);
         float2 w[C::R1 > 1 ? C::R1 : 2];
-        if (C::R1 > 1) twiddle_powers<C::R1>(tw1_base[2 * j], tw1_base[2 * j + 1], w);
+        if (C::R1 > 1 && !TAB) twiddle_powers<C::R1>(tw1_base[2 * j], tw1_base[2 * j + 1], w);
         XMR_UNROLL
         for (int c = 0; c < C::R1; ++c) {
             float2 z = v[j * C::R1 + bitrev(c, ilog2(C::R1))];
-            if (c > 0) z = cmul(z, w[c]);
+            if (c > 0) z = cmul(z, TAB ? tw1_tab[(c - 1) * C::R2 + b] : w[c]);
             B[c * C::PC + b * C::PB + k1] = z;
         }
     }
 }
-template <class C, bool INVERSE>
-XMR_HD void stage1(int t, const float2* A, float2* B, const float2* tw1_base /* [C1][2] */) {
+template <class C, bool INVERSE, bool TAB = false>
+XMR_HD void stage1(int t, const float2* A, float2* B, const float2* tw1_base /* [C1][2] */, const float2* tw1_tab = nullptr) {
     float2 v[C::E];
     stage1_load<C>(t, A, v);
-    stage1_store<C, INVERSE>(t, B, v, tw1_base);
+    stage1_store<C, INVERSE, TAB>(t, B, v, tw1_base, tw1_tab);
 }
 
 // ---- stage 2 -------------------------------------------------------------------------------------------

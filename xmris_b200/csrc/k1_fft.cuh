@@ -50,7 +50,8 @@ struct K1Smem {
     static constexpr size_t B = INPLACE_B ? 0 : size_t(C::SPB) * C::SIZE_B * sizeof(float2);
     static constexpr size_t RED = size_t(C::SPB) * 32 * 8;  // per group: up to 32 warps x (float, int)
     static constexpr size_t BAR = 64;
-    static constexpr size_t TOTAL = RING + B + RED + BAR;
+    static constexpr size_t TW1 = (C::R1 == 16 && C::R2 == 16) ? size_t(15 * 16) * sizeof(float2) : 0;   // stage-1 twiddle table
+    static constexpr size_t TOTAL = RING + B + RED + BAR + TW1;
 };
 
 template <int N>
@@ -90,6 +91,8 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
     float2* Bbuf = reinterpret_cast<float2*>(smem_raw + K1Smem<N>::RING);
     float* red = reinterpret_cast<float*>(smem_raw + K1Smem<N>::RING + K1Smem<N>::B);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + K1Smem<N>::RING + K1Smem<N>::B + K1Smem<N>::RED);
+    constexpr bool TW1_TAB = (K1Smem<N>::TW1 != 0);
+    float2* tw1_tab = TW1_TAB ? reinterpret_cast<float2*>(smem_raw + K1Smem<N>::RING + K1Smem<N>::B + K1Smem<N>::RED + K1Smem<N>::BAR) : nullptr;
 
     const int tid = threadIdx.x;
     const int g = tid / C::T;     // spectrum slot within the tile
@@ -144,6 +147,15 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
         }
     };
 
+    if (TW1_TAB) {
+        // W_M^(b*c) = W_N^(b*c*R0), c = 1..15, b = 0..15 (published by the barrier below / the first in-loop barrier)
+        for (int i = tid; i < 15 * 16; i += C::THREADS) {
+            const int c = i / 16 + 1, b = i % 16;
+            float2 w = p.twN[(b * c * C::R0) % C::N];
+            if (INVERSE) w.y = -w.y;
+            tw1_tab[i] = w;
+        }
+    }
     if (TMA) {
         if (tid == 0) {
             for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
@@ -190,9 +202,9 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
         if (IPB) {
             stage1_load<C>(t, my_slot, v);
             __syncthreads();                       // exchange B overwrites exchange A: every thread has its inputs
-            stage1_store<C, INVERSE>(t, my_B, v, tw1_base);
+            stage1_store<C, INVERSE, TW1_TAB>(t, my_B, v, tw1_base, tw1_tab);
         } else {
-            stage1<C, INVERSE>(t, my_slot, my_B, tw1_base);
+            stage1<C, INVERSE, TW1_TAB>(t, my_slot, my_B, tw1_base, tw1_tab);
         }
         __syncthreads();
         // separate buffers: the input slot is free again -> prefetch tile it+STAGES while stage 2 and the epilogue run
