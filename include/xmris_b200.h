@@ -74,6 +74,8 @@ int xmr_fid_to_spectrum_c64(const void* fid_dev, void* spec_dev, int64_t batch, 
  */
 int xmr_zero_fill_c64(const void* in_dev, void* out_dev, int64_t batch, int n_in, int n_out, int pad_left,
                       void* stream);
+ /* xmr_roll_rows_c64  replaces fftshift / ifftshift (fourier.py:31-32, 57-58) out[b, (k+shift) mod n] = in[b, k]        */
+int xmr_roll_rows_c64(const void* in_dev, void* out_dev, int64_t batch, int n, int shift, void* stream);
 int xmr_scale_rows_c64(const void* in_dev, void* out_dev, int64_t batch, int n, const float* w_dev, void* stream);
 int xmr_rotate_rows_c64(const void* in_dev, void* out_dev, int64_t batch, int n, const void* rot_dev, void* stream);
 

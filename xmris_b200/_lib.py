@@ -36,6 +36,7 @@ SIGNATURES = {
     "xmr_last_error": (ctypes.c_char_p, []),
     "xmr_fid_to_spectrum_c64": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _i, _d, _d, _vp]),
     "xmr_zero_fill_c64": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp]),
+    "xmr_roll_rows_c64": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "xmr_scale_rows_c64": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
     "xmr_rotate_rows_c64": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
     "xmr_phase_each_c64": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp]),

@@ -26,6 +26,25 @@ class XmrisB200Accessor:
     def to_hz(self, dim: str = DIMS.chemical_shift):
         return P.to_hz(self._obj, dim=dim)
 
+    # --- Fourier mixin (accessor.py:369-447) ---
+    def fft(self, dim=DIMS.time, out_dim=None):
+        return P.fft(self._obj, dim=dim, out_dim=out_dim)
+
+    def ifft(self, dim=DIMS.frequency, out_dim=None):
+        return P.ifft(self._obj, dim=dim, out_dim=out_dim)
+
+    def fftshift(self, dim):
+        return P.fftshift(self._obj, dim=dim)
+
+    def ifftshift(self, dim):
+        return P.ifftshift(self._obj, dim=dim)
+
+    def fftc(self, dim=DIMS.time, out_dim=None):
+        return P.fftc(self._obj, dim=dim, out_dim=out_dim)
+
+    def ifftc(self, dim=DIMS.frequency, out_dim=None):
+        return P.ifftc(self._obj, dim=dim, out_dim=out_dim)
+
     # --- processing (accessor.py:452-550) ---
     def apodize_exp(self, dim: str = DIMS.time, lb: float = 1.0):
         return P.apodize_exp(self._obj, dim=dim, lb=lb)

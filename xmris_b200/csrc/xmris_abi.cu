@@ -85,6 +85,17 @@ __global__ void zero_fill_kernel(const float2* __restrict__ in, float2* __restri
         out[i] = (k >= 0 && k < n_in) ? in[b * n_in + k] : make_float2(0.f, 0.f);
     }
 }
+// out[b, (k + shift) mod n] = in[b, k]  (np.roll along the last axis; fftshift / ifftshift, fourier.py:10-58)
+__global__ void roll_rows_kernel(const float2* __restrict__ in, float2* __restrict__ out, long long batch, int n, int shift) {
+    const long long total = batch * n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / n;
+        int k = int(i - b * n) - shift;       // destination index i <- source index k
+        if (k < 0) k += n;
+        out[i] = in[b * n + k];
+    }
+}
 __global__ void scale_rows_kernel(const float2* __restrict__ in, float2* __restrict__ out, long long batch, int n,
                                   const float* __restrict__ w) {
     const long long total = batch * n;
@@ -264,6 +275,18 @@ int xmr_zero_fill_c64(const void* in_dev, void* out_dev, int64_t batch, int n_in
         static_cast<const float2*>(in_dev), static_cast<float2*>(out_dev), batch, n_in, n_out, pad_left);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? XMR_OK : cuda_fail(e, "zero_fill launch");
+}
+
+int xmr_roll_rows_c64(const void* in_dev, void* out_dev, int64_t batch, int n, int shift, void* stream) {
+    if (batch < 0 || n < 0) return fail(XMR_ERR_BAD_ARG, "bad sizes");
+    if (batch == 0 || n == 0) return XMR_OK;
+    if (!in_dev || !out_dev || in_dev == out_dev) return fail(XMR_ERR_BAD_ARG, "NULL or aliased pointer");
+    shift %= n;
+    if (shift < 0) shift += n;
+    roll_rows_kernel<<<grid_for(batch * n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float2*>(in_dev), static_cast<float2*>(out_dev), batch, n, shift);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? XMR_OK : cuda_fail(e, "roll_rows launch");
 }
 
 int xmr_scale_rows_c64(const void* in_dev, void* out_dev, int64_t batch, int n, const float* w_dev, void* stream) {

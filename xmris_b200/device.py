@@ -258,6 +258,18 @@ def zero_fill(x, n_out, pad_left=0, stream=None):
     return out
 
 
+def roll_rows(x, shift, stream=None):
+    """``np.roll(x, shift, axis=-1)`` on the device (fftshift / ifftshift)."""
+    torch = _torch()
+    lib = _lib.load()
+    _require_cuda(x, "x")
+    n = x.shape[-1]
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.xmr_roll_rows_c64(_ptr(x), _ptr(out), x.numel() // max(n, 1), n, int(shift), _stream_ptr(stream)))
+    return out
+
+
 def scale_rows(x, weights, stream=None):
     """``x * weights`` along the last axis; ``weights`` float64 numpy (rounded to float32 on upload)."""
     torch = _torch()

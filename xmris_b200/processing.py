@@ -241,6 +241,96 @@ def to_fid(da, dim: str = DIMS.frequency, out_dim: str = DIMS.time):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# N1 fft / ifft / fftshift / ifftshift / fftc / ifftc                reference: processing/fourier.py:10-298
+# ---------------------------------------------------------------------------------------------------------
+
+
+def _as_list(dim):
+    return [dim] if isinstance(dim, str) else list(dim)
+
+
+def _shift(da, dim, which):
+    dims = _as_list(dim)
+    _check_dims(da, dims, which)
+    res = da
+    for d in dims:
+        n = res.sizes[d]
+        s = n // 2 if which == "fftshift" else (n + 1) // 2          # fourier.py:31 / :57
+        axis = res.get_axis_num(d)
+        out = D.roll_rows(_to_device(res.values, axis), s)
+        new = res.copy(data=_from_device(out, axis))
+        # roll_coords=True: every coordinate along d is rolled with the data
+        rolled = {}
+        for k in res.coords:
+            c = res.coords[k]
+            if d in c.dims:
+                rolled[k] = xr.Variable(c.dims, np.roll(np.asarray(c.values), s, axis=c.dims.index(d)), attrs=dict(c.attrs))
+        res = new.assign_coords(rolled) if rolled else new
+    return res
+
+
+def fftshift(da, dim):
+    """Roll data and coordinates by ``n//2`` along ``dim`` (``fourier.py:10-32``)."""
+    return _shift(da, dim, "fftshift")
+
+
+def ifftshift(da, dim):
+    """Roll data and coordinates by ``(n+1)//2`` along ``dim`` (``fourier.py:35-58``)."""
+    return _shift(da, dim, "ifftshift")
+
+
+def _transform(da, dim, out_dim, inverse, method):
+    dims = _as_list(dim)
+    _check_dims(da, dims, method)
+    out_dims = [out_dim] if isinstance(out_dim, str) else out_dim
+    if out_dims is not None and len(dims) != len(out_dims):
+        raise ValueError("`dim` and `out_dim` lists must have the same length.")
+    res = da
+    for i, d in enumerate(dims):
+        o_dim = out_dims[i] if out_dims else None
+        n = res.sizes[d]
+        old = np.asarray(res.coords[d].values)
+        delta = (old[1] - old[0]) if len(old) > 1 else 1.0             # fourier.py:95
+        new_coords = np.fft.fftfreq(n, d=delta)                        # unshifted reciprocal axis (fourier.py:98)
+        axis = res.get_axis_num(d)
+        out, _, _ = D.fid_to_spectrum(_to_device(res.values, axis), inverse=inverse, in_shift=0, out_shift=0)
+        res = res.copy(data=_from_device(out, axis))
+        target = o_dim if o_dim is not None else d
+        if not inverse and d == DIMS.time and o_dim in (None, DIMS.frequency):
+            var = as_variable(COORDS.frequency, target, new_coords)    # fourier.py:164-168
+        elif inverse and d == DIMS.frequency and o_dim in (None, DIMS.time):
+            var = as_variable(COORDS.time, target, new_coords)         # fourier.py:226-228
+        else:
+            var = xr.Variable(target, new_coords)
+        if o_dim is not None and o_dim != d:
+            res = res.rename({d: o_dim})
+        res = res.assign_coords({target: var})
+    return res
+
+
+def fft(da, dim=DIMS.time, out_dim=None):
+    """Ortho-normalised, unshifted FFT along ``dim`` (one or several dims) -- ``fourier.py:117-173``."""
+    return _transform(da, dim, out_dim, False, "fft")
+
+
+def ifft(da, dim=DIMS.frequency, out_dim=None):
+    """Ortho-normalised, unshifted inverse FFT -- ``fourier.py:176-232``."""
+    return _transform(da, dim, out_dim, True, "ifft")
+
+
+def fftc(da, dim=DIMS.time, out_dim=None):
+    """Centred FFT ``ifftshift -> fft -> fftshift`` (``fourier.py:238-266``)."""
+    new_dims = out_dim if out_dim is not None else dim
+    return fftshift(fft(ifftshift(da, dim=dim), dim=dim, out_dim=out_dim), dim=new_dims)
+
+
+def ifftc(da, dim=DIMS.frequency, out_dim=None):
+    """Centred inverse FFT ``ifftshift -> ifft -> fftshift`` (``fourier.py:269-298``)."""
+    new_dims = out_dim if out_dim is not None else dim
+    return fftshift(ifft(ifftshift(da, dim=dim), dim=dim, out_dim=out_dim), dim=new_dims)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # N3 to_ppm / to_hz -- coordinate-only, host metadata          reference: core/accessor.py:329-366
 # ---------------------------------------------------------------------------------------------------------
 
