@@ -92,4 +92,4 @@ def check(rc: int):
     msg = load().xmr_last_error().decode("utf-8", "replace")
     if rc in (XMR_ERR_BAD_ARG, XMR_ERR_UNSUPPORTED_N):
         raise ValueError(f"xmris_b200: {msg}")
-    raise RuntimeError(f"xmris_b200: {msg} (status {rc})")
+    raise RuntimeError(f"xmris_b200: {msg} (status {rc}) -- a working CUDA device is required; there is no CPU fallback")
