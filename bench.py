@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--ref-sample", type=int, default=65536, help="voxels per step of the --impl reference arm")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-per-voxel", action="store_true")
+    ap.add_argument("--per-voxel-batch", type=int, default=1 << 17, help="voxels per GPU for the mode=all side measurement")
     return ap.parse_args()
 
 
@@ -307,6 +309,29 @@ def run_ours(args):
         breakdown = {"pass1_stats_argmax_search_ms": float(np.mean([a.elapsed_time(b) for a, b, _ in parts])),
                      "pass2_store_phase_ms": float(np.mean([b.elapsed_time(c) for _, b, c in parts]))}
 
+    # ---- the per-voxel chain (autophase mode="all", kernel K2) on a bounded slice of the same workload -----------------
+    per_voxel = None
+    if args.mode == "single" and not args.no_per_voxel:
+        from xmris_b200 import pervoxel
+
+        nb = min(batch, args.per_voxel_batch)
+        pervoxel.chain_all_device(fid[:nb], t, None, "end", LB, out=out[:nb], peak_width=PEAK_WIDTH)
+        barrier()
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        for _ in range(2):
+            pervoxel.chain_all_device(fid[:nb], t, None, "end", LB, out=out[:nb], peak_width=PEAK_WIDTH)
+        pe1.record()
+        barrier()
+        pv_ms = pe0.elapsed_time(pe1) / 2
+        if dist is not None:
+            tm = torch.tensor([pv_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            pv_ms = float(tm.item())
+        per_voxel = {"value": world * nb / (pv_ms / 1e3), "unit": "spectra/s", "voxels_per_gpu": nb, "ms_per_step": pv_ms,
+                     "what": "same chain with autophase mode='all' (one fused kernel per voxel: FFT + in-CTA (p0,p1) search + "
+                             "phase); SFU/FP32-bound, see DESIGN.md K2"}
+
     # ---- e2e: pinned host buffers, H2D + chain + D2H inside the timed region ---------------------------------
     e2e = None
     if not args.no_e2e:
@@ -389,7 +414,7 @@ def run_ours(args):
         "config": {"workload": f"C5: {batch} voxels x {n}-pt FID per GPU -> {n}-pt spectrum, lb={LB}, full chain "
                                f"zero_fill(no-op)->apodize_exp->to_spectrum->autophase(mode={args.mode}, acme)",
                    "l2": "inputs (32 GiB/GPU) far exceed the 126 MB L2; no explicit flush", "autophase_mode": args.mode},
-        "roofline": roofline, "breakdown_ms": breakdown, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches["n"], "clocks": clocks,
+        "roofline": roofline, "breakdown_ms": breakdown, "per_voxel": per_voxel, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches["n"], "clocks": clocks,
         "result": {"p0": last[0], "p1": last[1], "pivot": last[2]} if args.mode == "single" else None,
     }
     print(json.dumps(line), flush=True)
