@@ -67,6 +67,17 @@ int xmr_fid_to_spectrum_c64(const void* fid_dev, void* spec_dev, int64_t batch, 
                             int inverse, int in_shift, int out_shift, float* absmax_dev, int* argmax_dev,
                             int phase_mode, double ph_a_turns, double ph_b_turns, void* stream);
 
+/* Pass 1 of autophase(mode="single"): per-spectrum max |S| for the GLOBAL argmax of phasing.py:229-231, with branch and
+ * bound: after the second FFT stage every output obeys |X|^2 <= 16 * sum_b max_c |Z[k1][c][b]|^2; spectra whose bound is
+ * below the running global maximum cannot hold the argmax and skip their last stage (absmax entry 0).  The global
+ * maximum and its first row are exact and run-independent.  running_max2_dev: one float of caller-owned scratch, shared
+ * by the chunks of one data set (reset_running_max = 1 on the first chunk).  Geometries outside the specialised path
+ * (zero filling, table windows, n_out > 4096) run the plain statistics pass.
+ */
+int xmr_fid_absmax_pruned_c64(const void* fid_dev, int64_t batch, int n_in, int n_out, int pad_left, int window_mode,
+                              const float* window_dev, const float* win_rows_host, float scale, float* absmax_dev,
+                              float* running_max2_dev, int reset_running_max, void* stream);
+
 /* Standalone elementwise ops for the un-fused accessor calls.
  * xmr_zero_fill_c64  replaces zero_fill   (fid.py:251)  out[b, pad_left + k] = in[b, k], zeros elsewhere
  * xmr_scale_rows_c64 replaces apodize_exp (fid.py:139)  out[b, k] = in[b, k] * w_dev[k]          (real weights)

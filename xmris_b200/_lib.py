@@ -35,6 +35,7 @@ SIGNATURES = {
     "xmr_version": (_i, []),
     "xmr_last_error": (ctypes.c_char_p, []),
     "xmr_fid_to_spectrum_c64": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _f, _i, _i, _i, _vp, _vp, _i, _d, _d, _vp]),
+    "xmr_fid_absmax_pruned_c64": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _i, _vp]),
     "xmr_zero_fill_c64": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp]),
     "xmr_roll_rows_c64": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "xmr_scale_rows_c64": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),

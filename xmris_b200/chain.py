@@ -71,8 +71,12 @@ def local_stats(fid_t, geo):
 
     Only the per-spectrum maxima are recorded (the cheapest statistics pass); the position of the maximum inside the
     winning row is recovered when that one row is transformed again for the search."""
-    _, absmax, _ = D.fid_to_spectrum(fid_t, n_out=geo["n_out"], pad_left=geo["pad_left"],
-                                     window=_win(geo, fid_t.device), store=False, want_stats=True, want_index=False)
+    if geo["n_out"] in D.SUPPORTED_N:
+        # branch and bound: spectra that provably cannot hold the global maximum skip their last FFT stage (entry 0)
+        absmax, _ = D.fid_absmax_pruned(fid_t, n_out=geo["n_out"], pad_left=geo["pad_left"], window=_win(geo, fid_t.device))
+    else:
+        _, absmax, _ = D.fid_to_spectrum(fid_t, n_out=geo["n_out"], pad_left=geo["pad_left"],
+                                         window=_win(geo, fid_t.device), store=False, want_stats=True, want_index=False)
     return D.global_argmax(absmax.reshape(-1), None, geo["n_out"])
 
 

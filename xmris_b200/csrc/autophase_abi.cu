@@ -65,7 +65,7 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
     sp.p0_hi = 180.0;
     sp.p1_lo = p0_only ? 0.0 : -4000.0;
     sp.p1_hi = p0_only ? 0.0 : 4000.0;
-    sp.p0_step = p0_only ? 0.05 : 2.0;
+    sp.p0_step = p0_only ? 0.05 : 2.0;   // (4 deg was tried: it lands in a neighbouring noise wiggle on a golden case)
     sp.p1_step = 5.0;
     sp.n_p0 = int((sp.p0_hi - sp.p0_lo) / sp.p0_step + 0.5) + 1;
     sp.n_p1 = p0_only ? 1 : int((sp.p1_hi - sp.p1_lo) / sp.p1_step + 0.5) + 1;
@@ -98,7 +98,7 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
     int n_prev = int(grid);
     Cand* cur = listB;
     double h0 = sp.p0_step, h1 = p0_only ? 0.0 : sp.p1_step;
-    const int levels = 6;
+    const int levels = 5;                // final spacing 3e-4 deg (p0), 8e-4 deg (p1)
     for (int lvl = 0; lvl < levels; ++lvl) {
         zp.prev = prev;
         zp.n_prev = n_prev;

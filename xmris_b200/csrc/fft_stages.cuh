@@ -83,22 +83,39 @@ XMR_HD void stage0_load(int t, const float2* slot, int n_in, int pad_left, int i
 // When pad_left != 0 (or in_shift is not a multiple of M) the loads above touch other threads' columns: the caller
 // must put a block barrier between stage0_load and stage0_store.  Otherwise each thread reads and writes the same
 // set of addresses and exchange A happens in place without a barrier.
+// stage0_compute leaves Y[k1][n2] (inter-stage twiddle applied) at v[j*R0 + k1]; stage0_write stores it as exchange A.
 template <class C, bool INVERSE, bool TW_PERSIST>
-XMR_HD void stage0_store(int t, float2* slot, float2* v /* [E] */, const float2* tw_persist /* [C0][R0-1] */,
-                         const float2* tw_base /* [C0][2] */) {
+XMR_HD void stage0_compute(int t, float2* v /* [E] */, const float2* tw_persist /* [C0][R0-1] */,
+                           const float2* tw_base /* [C0][2] */) {
     XMR_UNROLL
     for (int j = 0; j < C::C0; ++j) {
         dft_dif<C::R0, INVERSE>(v + j * C::R0);
-        const int n2 = t + C::T * j;
         float2 w[C::R0 > 1 ? C::R0 : 2];
         if (!TW_PERSIST && C::R0 > 1) twiddle_powers<C::R0>(tw_base[2 * j], tw_base[2 * j + 1], w);
+        float2 y[C::R0];
         XMR_UNROLL
         for (int k1 = 0; k1 < C::R0; ++k1) {
-            float2 y = v[j * C::R0 + bitrev(k1, ilog2(C::R0))];
-            if (k1 > 0) y = cmul(y, TW_PERSIST ? tw_persist[j * (C::R0 - 1) + k1 - 1] : w[k1]);
-            slot[k1 * C::M + n2] = y;
+            y[k1] = v[j * C::R0 + bitrev(k1, ilog2(C::R0))];
+            if (k1 > 0) y[k1] = cmul(y[k1], TW_PERSIST ? tw_persist[j * (C::R0 - 1) + k1 - 1] : w[k1]);
         }
+        XMR_UNROLL
+        for (int k1 = 0; k1 < C::R0; ++k1) v[j * C::R0 + k1] = y[k1];
     }
+}
+template <class C>
+XMR_HD void stage0_write(int t, float2* slot, const float2* v /* [E] */) {
+    XMR_UNROLL
+    for (int j = 0; j < C::C0; ++j) {
+        const int n2 = t + C::T * j;
+        XMR_UNROLL
+        for (int k1 = 0; k1 < C::R0; ++k1) slot[k1 * C::M + n2] = v[j * C::R0 + k1];
+    }
+}
+template <class C, bool INVERSE, bool TW_PERSIST>
+XMR_HD void stage0_store(int t, float2* slot, float2* v /* [E] */, const float2* tw_persist /* [C0][R0-1] */,
+                         const float2* tw_base /* [C0][2] */) {
+    stage0_compute<C, INVERSE, TW_PERSIST>(t, v, tw_persist, tw_base);
+    stage0_write<C>(t, slot, v);
 }
 
 // ---- stage 1 -------------------------------------------------------------------------------------------
@@ -116,22 +133,49 @@ XMR_HD void stage1_load(int t, const float2* A, float2* v /* [E] */) {
 }
 // tw1_tab (optional, shared memory): W_M^(b*c) at [(c-1)*R2 + b] -- 15 conflict-free 8-byte loads per butterfly instead of
 // a 14-multiply power chain (the FFT is issue-bound, the LSU has headroom).  nullptr: powers of tw1_base.
+// stage1_compute leaves Z[k1][c][b] at v[j*R1 + c] (natural order in c); stage1_write scatters it into exchange B.
 template <class C, bool INVERSE, bool TAB = false>
-XMR_HD void stage1_store(int t, float2* B, float2* v /* [E] */, const float2* tw1_base /* [C1][2] */,
-                         const float2* tw1_tab = nullptr) {
+XMR_HD void stage1_compute(int t, float2* v /* [E] */, const float2* tw1_base /* [C1][2] */, const float2* tw1_tab = nullptr) {
     XMR_UNROLL
     for (int j = 0; j < C::C1; ++j) {
-        const int beta = t + C::T * j, b = beta % C::R2, k1 = beta / C::R2;
+        const int b = (t + C::T * j) % C::R2;
         dft_dif<C::R1, INVERSE>(v + j * C::R1);
         float2 w[C::R1 > 1 ? C::R1 : 2];
         if (C::R1 > 1 && !TAB) twiddle_powers<C::R1>(tw1_base[2 * j], tw1_base[2 * j + 1], w);
+        float2 z[C::R1];
         XMR_UNROLL
         for (int c = 0; c < C::R1; ++c) {
-            float2 z = v[j * C::R1 + bitrev(c, ilog2(C::R1))];
-            if (c > 0) z = cmul(z, TAB ? tw1_tab[(c - 1) * C::R2 + b] : w[c]);
-            B[c * C::PC + b * C::PB + k1] = z;
+            z[c] = v[j * C::R1 + bitrev(c, ilog2(C::R1))];
+            if (c > 0) z[c] = cmul(z[c], TAB ? tw1_tab[(c - 1) * C::R2 + b] : w[c]);
         }
+        XMR_UNROLL
+        for (int c = 0; c < C::R1; ++c) v[j * C::R1 + c] = z[c];
     }
+}
+template <class C>
+XMR_HD void stage1_write(int t, float2* B, const float2* v /* [E] */) {
+    XMR_UNROLL
+    for (int j = 0; j < C::C1; ++j) {
+        const int beta = t + C::T * j, b = beta % C::R2, k1 = beta / C::R2;
+        XMR_UNROLL
+        for (int c = 0; c < C::R1; ++c) B[c * C::PC + b * C::PB + k1] = v[j * C::R1 + c];
+    }
+}
+// maxq (optional): receives max over this thread's exchange-B values of |z|^2 (branch-and-bound pruning in K1).
+template <class C, bool INVERSE, bool TAB = false, bool MAXQ = false>
+XMR_HD void stage1_store(int t, float2* B, float2* v /* [E] */, const float2* tw1_base /* [C1][2] */,
+                         const float2* tw1_tab = nullptr, float* maxq = nullptr) {
+    stage1_compute<C, INVERSE, TAB>(t, v, tw1_base, tw1_tab);
+    if (MAXQ) {
+        float mq = 0.f;
+        XMR_UNROLL
+        for (int i = 0; i < C::E; ++i) {
+            const float q = v[i].x * v[i].x + v[i].y * v[i].y;
+            mq = q > mq ? q : mq;
+        }
+        *maxq = mq;
+    }
+    stage1_write<C>(t, B, v);
 }
 template <class C, bool INVERSE, bool TAB = false>
 XMR_HD void stage1(int t, const float2* A, float2* B, const float2* tw1_base /* [C1][2] */, const float2* tw1_tab = nullptr) {

@@ -244,8 +244,9 @@ int xmr_chain_host_c64(const xmr_host_chain_desc* d, const void* fid_host, void*
             XMR_CUC(cudaMemcpyAsync(d_in_chunk(c), h_in + size_t(lo) * row_in, size_t(nb) * row_in, cudaMemcpyHostToDevice, w.s_in));
             XMR_CUC(cudaEventRecord(in_done[c], w.s_in));
             XMR_CUC(cudaStreamWaitEvent(w.s_cmp, in_done[c], 0));
-            XMR_RC(xmr_fid_to_spectrum_c64(d_in_chunk(c), nullptr, nb, n_in, n_out, d->pad_left, win_mode, win_dev, rows.data(), scale, 0,
-                                           0, n_out / 2, absmax + lo, nullptr, XMR_PHASE_NONE, 0.0, 0.0, w.s_cmp));
+            // branch-and-bound statistics: the running maximum (one float at o_arg + 32) is shared by the chunks of this call
+            XMR_RC(xmr_fid_absmax_pruned_c64(d_in_chunk(c), nb, n_in, n_out, d->pad_left, win_mode, win_dev, rows.data(), scale,
+                                             absmax + lo, reinterpret_cast<float*>(sm + o_arg + 32), c == 0 ? 1 : 0, w.s_cmp));
         }
         // ---- winner, its spectrum, the search ------------------------------------------------------------------------
         unsigned char* arg = sm + o_arg;

@@ -36,6 +36,7 @@ struct K1Params {
     double ph_a_turns;     // uniform phase: turns(m) = a + b*m
     double ph_b_turns;
     float2 ph_step[16];    // exp(2 pi i * b * R0*R1 * d), d < 16
+    float* run_max2;       // k1_max_kernel: running global max of |S|^2 (device scalar, zeroed by the launcher)
 };
 
 // N >= 8192: one shared buffer per spectrum serves as TMA landing slot, exchange A and exchange B ("in-place B"), one
@@ -257,7 +258,9 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
             if (F && !do_index) {
                 // max-only fast pass: one atomicMax per warp on the per-spectrum slot (zeroed by the launcher) instead of a
                 // block-wide reduction + barrier; non-negative floats order like their bit patterns.
-                if ((t & 31) == 0 && valid) atomicMax(reinterpret_cast<int*>(p.absmax + spec), __float_as_int(sqrtf(best)));
+                if ((t & 31) == 0 && valid) {
+                    atomicMax(reinterpret_cast<int*>(p.absmax + spec), __float_as_int(sqrtf(best)));
+                }
             } else if (C::T > 32) {
                 constexpr int WPG = C::T / 32;
                 float* rv = red + size_t(g) * 64;

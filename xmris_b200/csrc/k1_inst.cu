@@ -1,5 +1,6 @@
 // One instantiation set of K1 per transform length: compile with -DXMR_N=<N>.
 #include "k1_launch.cuh"
+#include "k1_max.cuh"
 
 #ifndef XMR_N
 #error "compile with -DXMR_N=<transform length>"
@@ -37,6 +38,35 @@ static cudaError_t launch_one(const K1Params& p, int max_ctas, cudaStream_t st) 
     return cudaGetLastError();
 }
 
+#if XMR_N >= 512 && XMR_N <= 4096
+static cudaError_t launch_max(const K1Params& p, cudaStream_t st) {
+    using C = FftCfg<XMR_N>;
+    auto kern = k1_max_kernel<XMR_N>;
+    constexpr size_t smem = K1MaxSmem<XMR_N>::TOTAL;
+    static thread_local int cached_dev = -1;
+    static thread_local int ctas_per_wave = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev != cached_dev) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        int per_sm = 0, sms = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        ctas_per_wave = (per_sm < 1 ? 1 : per_sm) * sms;
+        cached_dev = dev;
+    }
+    const long long ntiles = (p.batch + C::SPB - 1) / C::SPB;
+    const long long grid = ntiles < ctas_per_wave ? ntiles : ctas_per_wave;
+    if (grid < 1) return cudaSuccess;
+    kern<<<dim3((unsigned)grid), dim3(C::THREADS), smem, st>>>(p);
+    return cudaGetLastError();
+}
+#endif
+
 #define XMR_CAT2(a, b) a##b
 #define XMR_CAT(a, b) XMR_CAT2(a, b)
 
@@ -58,6 +88,9 @@ cudaError_t XMR_CAT(k1_launch_, XMR_N)(const K1Params& p, bool inverse, int win,
         if (!st_ && stats) {
             cudaError_t e = cudaMemsetAsync(p.absmax, 0, sizeof(float) * size_t(p.batch), st);   // atomicMax accumulators
             if (e != cudaSuccess) return e;
+#if XMR_N >= 512 && XMR_N <= 4096
+            if (p.run_max2 != nullptr) return launch_max(p, st);
+#endif
             return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STATS>(p, max_ctas, st);
         }
     }

@@ -1,0 +1,178 @@
+// K1-max: pass 1 of autophase(mode="single") -- per-spectrum max |S| for the global argmax (phasing.py:229-231), with
+// branch and bound.  Specialised for full-length input, separable window, fftshift-free statistics, N in [512, 4096].
+//
+// Two Cauchy-Schwarz bounds on every output of a spectrum, from partial transforms:
+//   level 0 (after the first FFT stage, M = 256 terms left):  |X|^2 <= M  * sum_n2 max_k1 |Y[k1][n2]|^2
+//   level 1 (after the second stage, 16 terms left):          |X|^2 <= 16 * sum_b  max_c  |Z[k1][c][b]|^2
+// (both are tight for a spectrum dominated by one line: all terms of the remaining sum then have equal magnitude).
+// If a bound is below the running global maximum the spectrum cannot hold the global argmax and the rest of its
+// transform is skipped -- after ONE stage and one barrier for most voxels of MRSI-like data.  The bounds never
+// under-estimate and the running maximum never exceeds the true one, so the global maximum and its first row are
+// exact and run-independent.
+//
+// Exchange B aliases the landing slot (no separate buffer), which pays for a 3-deep TMA ring at 2 CTAs/SM: with the
+// pruned spectra costing only two FFT stages, the pass is bound by HBM latency x bytes in flight, not by issue.
+#pragma once
+#include "k1_fft.cuh"
+
+namespace xmr {
+
+constexpr int K1MAX_STAGES = 3;
+
+template <int N>
+struct K1MaxSmem {
+    using C = FftCfg<N>;
+    static constexpr size_t SLOT = (C::SIZE_B > C::N ? C::SIZE_B : C::N);   // complex elements: holds A, then B
+    static constexpr size_t RING = size_t(K1MAX_STAGES) * C::SPB * SLOT * sizeof(float2);
+    static constexpr size_t RED = size_t(C::SPB) * 32 * sizeof(float) + 64;   // + the CTA's snapshot of the running maximum
+    static constexpr size_t BAR = 64;
+    static constexpr size_t TW1 = size_t(15 * 16) * sizeof(float2);
+    static constexpr size_t TOTAL = RING + RED + BAR + TW1;
+};
+
+template <int N>
+__global__ void __launch_bounds__(FftCfg<N>::THREADS, 2) k1_max_kernel(const __grid_constant__ K1Params p) {
+    using C = FftCfg<N>;
+    using SM = K1MaxSmem<N>;
+    static_assert(C::E == 16 && C::R1 == 16 && C::R2 == 16 && C::T >= 32, "k1_max_kernel: N in [512, 4096]");
+    constexpr int NTW = C::C0 * (C::R0 - 1);
+    constexpr int WPG = C::T / 32;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* ring = reinterpret_cast<float2*>(smem_raw);
+    float* red = reinterpret_cast<float*>(smem_raw + SM::RING);
+    float* run_s = red + C::SPB * 32;   // [2]: thread 0's read of the running maximum, double buffered by iteration parity
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + SM::RING + SM::RED);
+    float2* tw1_tab = reinterpret_cast<float2*>(smem_raw + SM::RING + SM::RED + SM::BAR);
+
+    const int tid = threadIdx.x, g = tid / C::T, t = tid % C::T;
+    const long long ntiles = (p.batch + C::SPB - 1) / C::SPB;
+
+    float2 tw_persist[NTW];
+    float2 tw0_base[C::C0 * 2], tw1_base[C::C1 * 2];
+    init_twiddles<C, false>(t, p.twN, tw_persist, tw0_base, tw1_base);
+    float wcol[C::C0];
+#pragma unroll
+    for (int j = 0; j < C::C0; ++j) wcol[j] = p.win ? p.win[t + C::T * j] : p.scale;
+    for (int i = tid; i < 15 * 16; i += C::THREADS) tw1_tab[i] = p.twN[((i % 16) * (i / 16 + 1) * C::R0) % C::N];
+
+    auto issue = [&](long long tile, int slot) {
+        const long long s0 = tile * C::SPB;
+        const int nvalid = int((p.batch - s0) < C::SPB ? (p.batch - s0) : C::SPB);
+        constexpr uint32_t row_bytes = uint32_t(C::N) * 8u;
+        mbar_arrive_expect_tx(&bars[slot], row_bytes * nvalid);
+        float2* dst = ring + size_t(slot) * C::SPB * SM::SLOT;
+        for (int r = 0; r < nvalid; ++r) bulk_g2s(dst + size_t(r) * SM::SLOT, p.in + (s0 + r) * C::N, row_bytes, &bars[slot]);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < K1MAX_STAGES; ++s) mbar_init(&bars[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < K1MAX_STAGES; ++s) {
+            const long long tile = blockIdx.x + (long long)s * gridDim.x;
+            if (tile < ntiles) issue(tile, s);
+        }
+    }
+
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int slot = it % K1MAX_STAGES;
+        const long long spec = tile * C::SPB + g;
+        const bool valid = spec < p.batch;
+        float2* my_slot = ring + (size_t(slot) * C::SPB + g) * SM::SLOT;
+        // ONE thread samples the (concurrently growing) running maximum and publishes it through shared memory: the skip
+        // decision gates block barriers, so every thread of the CTA must see the same value.
+        if (tid == 0) run_s[it & 1] = *reinterpret_cast<volatile float*>(p.run_max2);
+        mbar_wait(&bars[slot], (it / K1MAX_STAGES) & 1);
+
+        float2 v[C::E];
+        stage0_load<C, 2>(t, my_slot, valid ? C::N : 0, 0, 0, p.scale, p.win, wcol, p.win_rows, v);
+        stage0_compute<C, false, true>(t, v, tw_persist, tw0_base);
+        // ---- level-0 bound: |X|^2 <= M * sum_n2 max_k1 |Y[k1][n2]|^2  (Cauchy-Schwarz over the M = 256 remaining terms) --
+        float s0 = 0.f;
+#pragma unroll
+        for (int j = 0; j < C::C0; ++j) {
+            float m = 0.f;
+#pragma unroll
+            for (int k1 = 0; k1 < C::R0; ++k1) {
+                const float2 y = v[j * C::R0 + k1];
+                m = fmaxf(m, y.x * y.x + y.y * y.y);
+            }
+            s0 += m;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+        if ((t & 31) == 0) red[g * 32 + (t >> 5)] = s0;
+        __syncthreads();                       // also: every thread has read its part of the landing slot
+        const float run2 = run_s[it & 1];      // written before this barrier
+        bool skip_mine, skip_all = true;
+        {
+            float mine = 0.f;
+#pragma unroll
+            for (int gg = 0; gg < C::SPB; ++gg) {
+                float m = red[gg * 32];
+#pragma unroll
+                for (int w = 1; w < WPG; ++w) m += red[gg * 32 + w];
+                const bool sk = (float(C::M) * m * 1.0001f < run2);
+                skip_all = skip_all && sk;
+                if (gg == g) mine = sk ? 1.f : 0.f;
+            }
+            skip_mine = mine != 0.f;
+        }
+        if (!skip_all) {
+            // ---- survivors: exchange A, stage 1, level-1 bound |X|^2 <= 16 * sum_b max_c |Z[k1][c][b]|^2 -----------------
+            if (!skip_mine) stage0_write<C>(t, my_slot, v);
+            __syncthreads();
+            float mq = 0.f;
+            if (!skip_mine) {
+                stage1_load<C>(t, my_slot, v);
+                stage1_compute<C, false, true>(t, v, tw1_base, tw1_tab);
+#pragma unroll
+                for (int i = 0; i < C::E; ++i) mq = fmaxf(mq, v[i].x * v[i].x + v[i].y * v[i].y);
+#pragma unroll
+                for (int off = 1; off < 16; off <<= 1) mq += __shfl_xor_sync(0xffffffffu, mq, off);   // sum over b
+                mq = fmaxf(mq, __shfl_xor_sync(0xffffffffu, mq, 16));                                  // max over k1
+            }
+            if ((t & 31) == 0) red[g * 32 + (t >> 5)] = mq;
+            __syncthreads();                   // every survivor holds its exchange-A inputs: the slot may be reused
+            bool skip1_all = true, skip1_mine = true;
+#pragma unroll
+            for (int gg = 0; gg < C::SPB; ++gg) {
+                float m = red[gg * 32];
+#pragma unroll
+                for (int w = 1; w < WPG; ++w) m = fmaxf(m, red[gg * 32 + w]);
+                const bool sk = (16.0f * m * 1.0001f < run2);     // groups pruned at level 0 wrote 0 -> skipped here too
+                skip1_all = skip1_all && sk;
+                if (gg == g) skip1_mine = sk;
+            }
+            if (!skip1_all) {
+                if (!skip1_mine) stage1_write<C>(t, my_slot, v);
+                __syncthreads();
+                if (!skip1_mine) {
+                    stage2<C, false>(t, my_slot, v);
+                    float best = 0.f;
+#pragma unroll
+                    for (int i = 0; i < C::E; ++i) best = fmaxf(best, v[i].x * v[i].x + v[i].y * v[i].y);
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, off));
+                    if ((t & 31) == 0 && valid) {
+                        atomicMax(reinterpret_cast<int*>(p.absmax + spec), __float_as_int(sqrtf(best)));
+                        atomicMax(reinterpret_cast<int*>(p.run_max2), __float_as_int(best));
+                    }
+                }
+                __syncthreads();               // exchange B fully consumed before the slot is re-armed
+            }
+        }
+        if (tid == 0) {
+            const long long nt = tile + (long long)K1MAX_STAGES * gridDim.x;
+            if (nt < ntiles) {
+                fence_proxy_async_smem();
+                issue(nt, slot);
+            }
+        }
+    }
+}
+
+}  // namespace xmr

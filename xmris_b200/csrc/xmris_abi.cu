@@ -184,10 +184,10 @@ extern "C" {
 int xmr_version(void) { return 100; }
 const char* xmr_last_error(void) { return xmr_abi::g_err; }
 
-int xmr_fid_to_spectrum_c64(const void* fid_dev, void* spec_dev, int64_t batch, int n_in, int n_out, int pad_left,
-                            int window_mode, const float* window_dev, const float* win_rows_host, float scale,
-                            int inverse, int in_shift, int out_shift, float* absmax_dev, int* argmax_dev,
-                            int phase_mode, double ph_a_turns, double ph_b_turns, void* stream) {
+static int k1_dispatch(const void* fid_dev, void* spec_dev, int64_t batch, int n_in, int n_out, int pad_left,
+                       int window_mode, const float* window_dev, const float* win_rows_host, float scale,
+                       int inverse, int in_shift, int out_shift, float* absmax_dev, int* argmax_dev,
+                       int phase_mode, double ph_a_turns, double ph_b_turns, float* run_max2, void* stream) {
     if (!supported_n(n_out))
         return fail(XMR_ERR_UNSUPPORTED_N, "n_out=%d: transform length must be a power of two in [16, 8192]", n_out);
     if (batch < 0 || n_in < 1 || n_in > n_out || pad_left < 0 || pad_left + n_in > n_out)
@@ -229,6 +229,7 @@ int xmr_fid_to_spectrum_c64(const void* fid_dev, void* spec_dev, int64_t batch, 
     p.scale = scale;
     p.absmax = absmax_dev;
     p.argmax = argmax_dev;
+    p.run_max2 = run_max2;
     const int r0 = n_out >= 256 ? n_out / 256 : 1;
     for (int i = 0; i < 32; ++i) p.win_rows[i] = 1.0f;
     int win = 2;
@@ -262,6 +263,26 @@ int xmr_fid_to_spectrum_c64(const void* fid_dev, void* spec_dev, int64_t batch, 
     }
     if (e != cudaSuccess) return cuda_fail(e, "k1 launch");
     return XMR_OK;
+}
+
+int xmr_fid_to_spectrum_c64(const void* fid_dev, void* spec_dev, int64_t batch, int n_in, int n_out, int pad_left,
+                            int window_mode, const float* window_dev, const float* win_rows_host, float scale,
+                            int inverse, int in_shift, int out_shift, float* absmax_dev, int* argmax_dev,
+                            int phase_mode, double ph_a_turns, double ph_b_turns, void* stream) {
+    return k1_dispatch(fid_dev, spec_dev, batch, n_in, n_out, pad_left, window_mode, window_dev, win_rows_host, scale, inverse,
+                       in_shift, out_shift, absmax_dev, argmax_dev, phase_mode, ph_a_turns, ph_b_turns, nullptr, stream);
+}
+
+int xmr_fid_absmax_pruned_c64(const void* fid_dev, int64_t batch, int n_in, int n_out, int pad_left, int window_mode,
+                              const float* window_dev, const float* win_rows_host, float scale, float* absmax_dev,
+                              float* running_max2_dev, int reset_running_max, void* stream) {
+    if (!absmax_dev || !running_max2_dev) return fail(XMR_ERR_BAD_ARG, "NULL pointer");
+    if (reset_running_max) {
+        cudaError_t e = cudaMemsetAsync(running_max2_dev, 0, sizeof(float), static_cast<cudaStream_t>(stream));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(running max)");
+    }
+    return k1_dispatch(fid_dev, nullptr, batch, n_in, n_out, pad_left, window_mode, window_dev, win_rows_host, scale, 0, 0,
+                       n_out / 2, absmax_dev, nullptr, XMR_PHASE_NONE, 0.0, 0.0, running_max2_dev, stream);
 }
 
 int xmr_zero_fill_c64(const void* in_dev, void* out_dev, int64_t batch, int n_in, int n_out, int pad_left,

@@ -241,6 +241,40 @@ def fid_to_spectrum(fid, n_out=None, pad_left=0, window=None, scale=None, invers
     return spec, absmax, argmax
 
 
+def fid_absmax_pruned(fid, n_out=None, pad_left=0, window=None, absmax=None, running=None, reset=True, stream=None):
+    """Per-spectrum ``max |S|`` for the global-argmax pass with branch-and-bound pruning (entries of spectra that provably
+    cannot hold the global maximum are 0).  ``running``: 1-element float32 CUDA tensor shared by the chunks of one data set.
+    Returns ``(absmax, running)``."""
+    torch = _torch()
+    lib = _lib.load()
+    _require_cuda(fid, "fid")
+    n_in = fid.shape[-1]
+    n_out = n_in if n_out is None else int(n_out)
+    if n_out not in SUPPORTED_N:
+        raise ValueError("fid_absmax_pruned needs a power-of-two transform length")
+    batch = fid.numel() // n_in
+    dev = fid.device
+    if absmax is None:
+        absmax = torch.empty(tuple(fid.shape[:-1]), dtype=torch.float32, device=dev)
+    if running is None:
+        running = torch.zeros(1, dtype=torch.float32, device=dev)
+    win_mode, win_dev, rows = _lib.WIN_NONE, None, None
+    if isinstance(window, PreparedWindow):
+        win_mode, win_dev, rows = window.mode, window.dev, window.rows
+    elif window is not None:
+        win_mode, table, rows = split_window(window, n_out)
+        win_dev = torch.from_numpy(np.ascontiguousarray(table)).to(dev)
+    rows_arr = (ctypes.c_float * 32)(*([1.0] * 32))
+    if rows is not None:
+        for i, r in enumerate(rows):
+            rows_arr[i] = float(r)
+    with torch.cuda.device(dev):
+        _lib.check(lib.xmr_fid_absmax_pruned_c64(_ptr(fid), batch, n_in, n_out, int(pad_left), win_mode, _ptr(win_dev),
+                                                 ctypes.cast(rows_arr, ctypes.c_void_p), ctypes.c_float(1.0 / math.sqrt(n_out)),
+                                                 _ptr(absmax), _ptr(running), int(bool(reset)), _stream_ptr(stream)))
+    return absmax, running
+
+
 # ---------------------------------------------------------------------------------------------------------
 # un-fused elementwise pieces (each accessor call on its own)
 # ---------------------------------------------------------------------------------------------------------

@@ -36,6 +36,7 @@ class HostChain:
         self.d_ins = [torch.empty((batch, n_in), dtype=torch.complex64, device=device) for _ in range(2)]
         self.absmaxs = [torch.empty(batch, dtype=torch.float32, device=device) for _ in range(2)]
         self.d_in, self.absmax = self.d_ins[0], self.absmaxs[0]
+        self.running = [torch.zeros(1, dtype=torch.float32, device=device) for _ in range(2)]
         self.d_out = [torch.empty((self.chunk, self.n_out), dtype=torch.complex64, device=device) for _ in range(2)]
         self.h2d_bytes = batch * n_in * 8
         self.d2h_bytes = batch * self.n_out * 8
@@ -55,6 +56,7 @@ class HostChain:
         geo, win = self.geo, chain._win(self.geo, self.dev)
         d_in, absmax = self.d_ins[k], self.absmaxs[k]
         done = []
+        first = True
         for lo, hi in self._chunks():
             with torch.cuda.stream(self.s_in):
                 d_in[lo:hi].copy_(h_in[lo:hi], non_blocking=True)
@@ -65,9 +67,15 @@ class HostChain:
                 # statistics run on their own stream so that batch i+1's pass 1 never queues in front of batch i's pass 2
                 with torch.cuda.stream(self.s_a):
                     self.s_a.wait_event(ev)
-                    _, am, _ = D.fid_to_spectrum(d_in[lo:hi], n_out=self.n_out, pad_left=geo["pad_left"], window=win,
-                                                 store=False, want_stats=True, want_index=False)
-                    absmax[lo:hi].copy_(am, non_blocking=True)
+                    if self.n_out in D.SUPPORTED_N:
+                        # the running maximum is shared by the chunks of this batch (reset on the first one)
+                        D.fid_absmax_pruned(d_in[lo:hi], n_out=self.n_out, pad_left=geo["pad_left"], window=win,
+                                            absmax=absmax[lo:hi], running=self.running[k], reset=first)
+                    else:
+                        _, am, _ = D.fid_to_spectrum(d_in[lo:hi], n_out=self.n_out, pad_left=geo["pad_left"], window=win,
+                                                     store=False, want_stats=True, want_index=False)
+                        absmax[lo:hi].copy_(am, non_blocking=True)
+                    first = False
         if self.mode == "single":
             ev = torch.cuda.Event()
             ev.record(self.s_a)
