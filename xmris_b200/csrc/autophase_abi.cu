@@ -94,6 +94,9 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
     zp.p1_lo = sp.p1_lo;
     zp.p1_hi = sp.p1_hi;
     zp.rows = p0_only ? 1 : ZOOM_SIDE;
+    zp.n_starts = ZOOM_STARTS;
+    zp.sep0 = 2.0 * sp.p0_step;
+    zp.sep1 = p0_only ? 0.0 : 2.0 * sp.p1_step;
     const Cand* prev = listA;
     int n_prev = int(grid);
     Cand* cur = listB;
@@ -105,17 +108,18 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
         zp.cur = cur;
         zp.h0 = h0;
         zp.h1 = h1;
-        const int zgrid = zp.rows * ZOOM_CHUNKS;
-        search_zoom_kernel<METHOD><<<zgrid, SEARCH_THREADS, smem_zoom, st>>>(zp);
+        zp.first_level = (lvl == 0) ? 1 : 0;
+        const int per_start = zp.rows * ZOOM_CHUNKS;
+        search_zoom_kernel<METHOD><<<per_start * ZOOM_STARTS, SEARCH_THREADS, smem_zoom, st>>>(zp);
         e = cudaGetLastError();
         if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_zoom launch");
-        n_prev = zgrid * SEARCH_K;
+        n_prev = per_start * SEARCH_K;                 // candidates per start
         prev = cur;
         cur = (cur == listB) ? listA : listB;
         h0 /= 5.0;
         h1 /= 5.0;
     }
-    search_finalize_kernel<<<1, SEARCH_THREADS, 0, st>>>(prev, n_prev, result);
+    search_finalize_kernel<<<1, SEARCH_THREADS, 0, st>>>(prev, n_prev * ZOOM_STARTS, result);
     e = cudaGetLastError();
     if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_finalize launch");
     return XMR_OK;

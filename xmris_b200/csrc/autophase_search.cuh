@@ -101,14 +101,27 @@ struct ZoomParams {
     double h0, h1;      // half-widths of this level's window around the best previous candidate
     double p0_lo, p0_hi, p1_lo, p1_hi;
     int rows;           // 21 (two parameters) or 1 (p0 only)
-    Cand* cur;          // rows * 3 * SEARCH_K candidates
+    Cand* cur;          // n_starts * rows * 3 * SEARCH_K candidates (one contiguous block per start)
+    int n_starts;       // basins refined in parallel (ZOOM_STARTS)
+    int first_level;    // 1: prev is the coarse list shared by all starts (start s takes the s-th best DISTINCT cell);
+                        // 0: prev holds one block of n_prev candidates per start
+    double sep0, sep1;  // first level: two cells are distinct when they differ by more than this in p0 or in p1
 };
 
+constexpr int ZOOM_STARTS = 2;  // the two best distinct coarse cells are refined side by side (one wave of 126 CTAs)
 constexpr int ZOOM_SIDE = 21;   // 21 x 21 points per level, spacing h/10
 constexpr int ZOOM_CHUNKS = 3;  // 3 * SEARCH_K = 24 >= 21
 
-// block-wide argmin of a candidate list (lowest index wins ties) -> broadcast
-__device__ __forceinline__ Cand block_argmin(const Cand* list, int n_list) {
+__device__ __forceinline__ bool cand_distinct(const Cand& a, const Cand& b, double sep0, double sep1) {
+    double d0 = fabs(a.p0 - b.p0);
+    d0 = fmin(d0, 360.0 - d0);                       // p0 is periodic
+    return d0 > sep0 || fabs(a.p1 - b.p1) > sep1;
+}
+
+// block-wide argmin of a candidate list (lowest index wins ties) -> broadcast.  `excl` (optional): skip candidates that
+// are not distinct from it.
+__device__ __forceinline__ Cand block_argmin(const Cand* list, int n_list, const Cand* excl = nullptr, double sep0 = 0.0,
+                                             double sep1 = 0.0) {
     __shared__ double sf[SEARCH_THREADS / 32];
     __shared__ int si[SEARCH_THREADS / 32];
     __shared__ int s_best;
@@ -116,6 +129,7 @@ __device__ __forceinline__ Cand block_argmin(const Cand* list, int n_list) {
     int idx = 0x7fffffff;
     for (int i = threadIdx.x; i < n_list; i += blockDim.x) {
         const double v = list[i].f;
+        if (excl != nullptr && !cand_distinct(list[i], *excl, sep0, sep1)) continue;
         if (v < f || (v == f && i < idx)) { f = v; idx = i; }
     }
 #pragma unroll
@@ -129,10 +143,17 @@ __device__ __forceinline__ Cand block_argmin(const Cand* list, int n_list) {
     if (threadIdx.x == 0) {
         for (int w = 1; w < int(blockDim.x >> 5); ++w)
             if (sf[w] < f || (sf[w] == f && si[w] < idx)) { f = sf[w]; idx = si[w]; }
-        s_best = (idx == 0x7fffffff) ? 0 : idx;
+        s_best = (idx == 0x7fffffff) ? -1 : idx;
     }
     __syncthreads();
-    return list[s_best];
+    const int b = s_best;
+    __syncthreads();                                  // s_best may be rewritten by a second call
+    if (b < 0) {                                      // nothing (finite / distinct) found
+        Cand none = list[0];
+        none.f = CUDART_INF;
+        return none;
+    }
+    return list[b];
 }
 
 // ---- zoom level: one CTA per (p1 row, chunk of K p0 values), float64, the 8 warps split the spectrum ---------
@@ -147,9 +168,21 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_zoom_kernel(const __gri
     const int L = (per_warp + 31) / 32;
     const int padshift = ilog2_ceil(L);
     load_padded(sp, p.spec, n, padshift);
-    const Cand centre = block_argmin(p.prev, p.n_prev);   // contains the barriers that also publish `sp`
+    const int per_start = p.rows * ZOOM_CHUNKS;
+    const int start = blockIdx.x / per_start, local = blockIdx.x % per_start;
+    Cand centre;                                          // (block_argmin contains the barriers that also publish `sp`)
+    if (p.first_level) {
+        centre = block_argmin(p.prev, p.n_prev);
+        for (int s = 1; s <= start; ++s) {                // the (start+1)-th best cell that is distinct from the best one
+            const Cand first = centre;
+            centre = block_argmin(p.prev, p.n_prev, &first, p.sep0, p.sep1);
+        }
+    } else {
+        centre = block_argmin(p.prev + (size_t)start * p.n_prev, p.n_prev);
+    }
+    const bool dead = !(centre.f < CUDART_INF);           // no second basin: this start reports +inf
 
-    const int row = blockIdx.x / ZOOM_CHUNKS, ch = blockIdx.x % ZOOM_CHUNKS;
+    const int row = local / ZOOM_CHUNKS, ch = local % ZOOM_CHUNKS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double p1 = (p.rows == 1) ? centre.p1
                                     : fmin(fmax(centre.p1 + (row - ZOOM_SIDE / 2) * (p.h1 / (ZOOM_SIDE / 2)), p.p1_lo), p.p1_hi);
@@ -187,7 +220,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_zoom_kernel(const __gri
         }
         Cand c;
         c.f = tot.score(0, p.geom);
-        if (!(c.f == c.f)) c.f = CUDART_INF;   // NaN never wins
+        if (!(c.f == c.f) || dead) c.f = CUDART_INF;   // NaN never wins
         // select p0k[k] without dynamic register indexing
         double myp0 = p0k[0];
 #pragma unroll
