@@ -1,17 +1,18 @@
 // K1-max: pass 1 of autophase(mode="single") -- per-spectrum max |S| for the global argmax (phasing.py:229-231), with
 // branch and bound.  Specialised for full-length input, separable window, fftshift-free statistics, N in [512, 4096].
 //
-// Two Cauchy-Schwarz bounds on every output of a spectrum, from partial transforms:
-//   level 0 (after the first FFT stage, M = 256 terms left):  |X|^2 <= M  * sum_n2 max_k1 |Y[k1][n2]|^2
-//   level 1 (after the second stage, 16 terms left):          |X|^2 <= 16 * sum_b  max_c  |Z[k1][c][b]|^2
-// (both are tight for a spectrum dominated by one line: all terms of the remaining sum then have equal magnitude).
-// If a bound is below the running global maximum the spectrum cannot hold the global argmax and the rest of its
-// transform is skipped -- after ONE stage and one barrier for most voxels of MRSI-like data.  The bounds never
-// under-estimate and the running maximum never exceeds the true one, so the global maximum and its first row are
-// exact and run-independent.
+// Two upper bounds on every output of a spectrum, each far cheaper than finishing the transform:
+//   level 0 (no transform):                          |X| <= sum_n |x_n| |w_n|                      (triangle inequality)
+//   level 1 (after two FFT stages, 16 terms left):   |X|^2 <= 16 * sum_b max_c |Z[k1][c][b]|^2     (Cauchy-Schwarz)
+// On decaying multi-line FIDs level 0 is within ~1.2x of the spectrum's own maximum (a Cauchy-Schwarz bound after one
+// radix-16 stage: ~1.5x, at ten times the instructions) and level 1 within ~1.02x.  If a bound is below the running
+// global maximum the spectrum cannot hold the global argmax and the rest of its work is skipped: ~3/4 of the voxels of
+// MRSI-like data cost one pass over their samples (4 instructions per point, HBM-bound), most of the others two FFT
+// stages, < 1 % a full transform.  The bounds never under-estimate (float32 rounding is covered by the 1.0001 margin)
+// and the running maximum never exceeds the true one, so the global maximum and its first row are exact and
+// run-independent.
 //
-// Exchange B aliases the landing slot (no separate buffer), which pays for a 3-deep TMA ring at 2 CTAs/SM: with the
-// pruned spectra costing only two FFT stages, the pass is bound by HBM latency x bytes in flight, not by issue.
+// Exchange B aliases the landing slot (no separate buffer), which pays for a 3-deep TMA ring at 2 CTAs/SM.
 #pragma once
 #include "k1_fft.cuh"
 
@@ -87,24 +88,25 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, 2) k1_max_kernel(const __g
         if (tid == 0) run_s[it & 1] = *reinterpret_cast<volatile float*>(p.run_max2);
         mbar_wait(&bars[slot], (it / K1MAX_STAGES) & 1);
 
+        // ---- level-0 bound (no transform at all): |X_k| = |sum_n x_n w_n e^{..}| <= sum_n |x_n| w_n  (triangle inequality).
+        // On decaying multi-line FIDs this L1 norm is within ~1.2x of the spectrum's own maximum -- tighter than the
+        // Cauchy-Schwarz bound after a first radix-16 stage (~1.5x) at a tenth of the instructions.
         float2 v[C::E];
-        stage0_load<C, 2>(t, my_slot, valid ? C::N : 0, 0, 0, p.scale, p.win, wcol, p.win_rows, v);
-        stage0_compute<C, false, true>(t, v, tw_persist, tw0_base);
-        // ---- level-0 bound: |X|^2 <= M * sum_n2 max_k1 |Y[k1][n2]|^2  (Cauchy-Schwarz over the M = 256 remaining terms) --
-        float s0 = 0.f;
+        float l1 = 0.f;
 #pragma unroll
         for (int j = 0; j < C::C0; ++j) {
-            float m = 0.f;
+            float cj = 0.f;
 #pragma unroll
-            for (int k1 = 0; k1 < C::R0; ++k1) {
-                const float2 y = v[j * C::R0 + k1];
-                m = fmaxf(m, y.x * y.x + y.y * y.y);
+            for (int n1 = 0; n1 < C::R0; ++n1) {
+                const float2 x = valid ? my_slot[C::M * n1 + t + C::T * j] : make_float2(0.f, 0.f);
+                v[j * C::R0 + n1] = x;
+                cj = fmaf(sqrt_approx(fmaf(x.x, x.x, x.y * x.y)), fabsf(p.win_rows[n1]), cj);
             }
-            s0 += m;
+            l1 = fmaf(cj, fabsf(wcol[j]), l1);
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, off);
-        if ((t & 31) == 0) red[g * 32 + (t >> 5)] = s0;
+        for (int off = 16; off > 0; off >>= 1) l1 += __shfl_xor_sync(0xffffffffu, l1, off);
+        if ((t & 31) == 0) red[g * 32 + (t >> 5)] = l1;
         __syncthreads();                       // also: every thread has read its part of the landing slot
         const float run2 = run_s[it & 1];      // written before this barrier
         bool skip_mine, skip_all = true;
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, 2) k1_max_kernel(const __g
                 float m = red[gg * 32];
 #pragma unroll
                 for (int w = 1; w < WPG; ++w) m += red[gg * 32 + w];
-                const bool sk = (float(C::M) * m * 1.0001f < run2);
+                const bool sk = (m * m * 1.0001f < run2);
                 skip_all = skip_all && sk;
                 if (gg == g) mine = sk ? 1.f : 0.f;
             }
@@ -123,7 +125,14 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, 2) k1_max_kernel(const __g
         }
         if (!skip_all) {
             // ---- survivors: exchange A, stage 1, level-1 bound |X|^2 <= 16 * sum_b max_c |Z[k1][c][b]|^2 -----------------
-            if (!skip_mine) stage0_write<C>(t, my_slot, v);
+            if (!skip_mine) {
+#pragma unroll
+                for (int j = 0; j < C::C0; ++j)
+#pragma unroll
+                    for (int n1 = 0; n1 < C::R0; ++n1) v[j * C::R0 + n1] = cscale(v[j * C::R0 + n1], wcol[j] * p.win_rows[n1]);
+                stage0_compute<C, false, true>(t, v, tw_persist, tw0_base);
+                stage0_write<C>(t, my_slot, v);
+            }
             __syncthreads();
             float mq = 0.f;
             if (!skip_mine) {

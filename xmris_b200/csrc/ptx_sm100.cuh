@@ -54,6 +54,12 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
                  "r"(smem_u32(src_smem)), "r"(bytes)
                  : "memory");
 }
+// one MUFU.SQRT (max relative error 2^-23)
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
