@@ -114,6 +114,14 @@ int xmr_row_absmax_c64(const void* spec_dev, int64_t batch, int n, float* absmax
  *   workspace_dev at least xmr_autophase_workspace_bytes() bytes of device memory, caller-owned
  */
 int64_t xmr_autophase_workspace_bytes(void);
+/* Geometry of the search (process-wide; not part of the reference's interface -- the reference exposes the optimiser's
+ * knobs through **kwargs of differential_evolution, phasing.py:276-284): coarse grid steps in degrees, number of
+ * mutually distinct coarse cells refined side by side (<= 8), nested 21x21 zoom levels, how many leading
+ * levels run in float32, how many basins the remaining float64 levels keep, and the window shrink factor between zoom
+ * levels 0 and 1 (5 between all later ones; each level's window = +-`half-width`, spacing half-width/10).
+ * Defaults: 6, 15, 4, 4, 2, 2, 2.5 (final spacing 0.01 x 0.024 deg). */
+int xmr_autophase_search_tuning(double p0_step_deg, double p1_step_deg, int starts, int levels, int f32_levels,
+                                int late_starts, double first_ratio);
 int xmr_autophase_search_c64(const void* spec_dev, int n, double u0, double du, int method, int target_idx,
                              int index_width, int p0_only, double* result_dev, void* workspace_dev, void* stream);
 

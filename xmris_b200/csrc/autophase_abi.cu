@@ -35,6 +35,17 @@ __global__ void row_absmax_kernel(const float2* __restrict__ spec, long long bat
 
 constexpr int WS_LIST = 4096;   // candidates per ping-pong list
 
+// Search geometry (xmr_autophase_search_tuning): coarse grid steps in degrees, number of distinct coarse cells refined
+// side by side, nested zoom levels (each shrinks the window by 5).
+struct SearchTuning {
+    double p0_step = 6.0, p1_step = 15.0;
+    int starts = 4, levels = 4;
+    int f32_levels = 2;      // leading zoom levels evaluated in float32 (all `starts` basins)
+    int late_starts = 2;     // basins kept for the float64 levels
+    double first_ratio = 2.5;   // window shrink factor from zoom level 0 to level 1 (5 between all later levels)
+};
+SearchTuning g_tuning;
+
 template <int METHOD>
 int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, int p0_only, double* result, Cand* ws,
                cudaStream_t st) {
@@ -49,8 +60,10 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
     cudaError_t e;
     e = cudaFuncSetAttribute(search_coarse_kernel<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_coarse));
     if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "cudaFuncSetAttribute(search_coarse)");
-    e = cudaFuncSetAttribute(search_zoom_kernel<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_zoom));
+    e = cudaFuncSetAttribute(search_zoom_kernel<METHOD, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_zoom));
     if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "cudaFuncSetAttribute(search_zoom)");
+    e = cudaFuncSetAttribute(search_zoom_kernel<METHOD, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_zoom));
+    if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "cudaFuncSetAttribute(search_zoom f32)");
 
     Cand* listA = ws;
     Cand* listB = ws + WS_LIST;
@@ -65,8 +78,8 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
     sp.p0_hi = 180.0;
     sp.p1_lo = p0_only ? 0.0 : -4000.0;
     sp.p1_hi = p0_only ? 0.0 : 4000.0;
-    sp.p0_step = p0_only ? 0.05 : 2.0;   // (4 deg was tried: it lands in a neighbouring noise wiggle on a golden case)
-    sp.p1_step = 5.0;
+    sp.p0_step = p0_only ? 0.05 : g_tuning.p0_step;
+    sp.p1_step = g_tuning.p1_step;
     sp.n_p0 = int((sp.p0_hi - sp.p0_lo) / sp.p0_step + 0.5) + 1;
     sp.n_p1 = p0_only ? 1 : int((sp.p1_hi - sp.p1_lo) / sp.p1_step + 0.5) + 1;
     sp.out = listA;
@@ -78,7 +91,7 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
     long long grid = (items + 7) / 8;
     const long long cap = (long long)sms * 2;
     if (grid > cap) grid = cap;
-    if (grid > WS_LIST) grid = WS_LIST;
+    if (grid * (SEARCH_THREADS / 32) > WS_LIST) grid = WS_LIST / (SEARCH_THREADS / 32);
     search_coarse_kernel<METHOD><<<int(grid), SEARCH_THREADS, smem_coarse, st>>>(sp);
     e = cudaGetLastError();
     if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_coarse launch");
@@ -94,32 +107,52 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
     zp.p1_lo = sp.p1_lo;
     zp.p1_hi = sp.p1_hi;
     zp.rows = p0_only ? 1 : ZOOM_SIDE;
-    zp.n_starts = ZOOM_STARTS;
-    zp.sep0 = 2.0 * sp.p0_step;
-    zp.sep1 = p0_only ? 0.0 : 2.0 * sp.p1_step;
     const Cand* prev = listA;
-    int n_prev = int(grid);
+    int n_prev = int(grid) * (SEARCH_THREADS / 32);      // the coarse list: one best cell per warp
     Cand* cur = listB;
     double h0 = sp.p0_step, h1 = p0_only ? 0.0 : sp.p1_step;
-    const int levels = 5;                // final spacing 3e-4 deg (p0), 8e-4 deg (p1)
+    zp.sep0 = 2.0 * sp.p0_step;
+    zp.sep1 = p0_only ? 0.0 : 2.0 * sp.p1_step;
+    const int levels = g_tuning.levels;
+    const int per_start = zp.rows * ZOOM_CHUNKS;
+    int starts_prev = 0;
+    double ratio_prev = 1.0;
     for (int lvl = 0; lvl < levels; ++lvl) {
+        const bool f32 = lvl < g_tuning.f32_levels;
+        const int n_starts = f32 ? g_tuning.starts : (g_tuning.late_starts < g_tuning.starts ? g_tuning.late_starts : g_tuning.starts);
+        zp.n_starts = n_starts;
         zp.prev = prev;
-        zp.n_prev = n_prev;
         zp.cur = cur;
         zp.h0 = h0;
         zp.h1 = h1;
-        zp.first_level = (lvl == 0) ? 1 : 0;
-        const int per_start = zp.rows * ZOOM_CHUNKS;
-        search_zoom_kernel<METHOD><<<per_start * ZOOM_STARTS, SEARCH_THREADS, smem_zoom, st>>>(zp);
+        if (lvl == 0) {
+            zp.first_level = 1;
+            zp.n_prev = n_prev;
+        } else if (n_starts != starts_prev) {
+            // fewer basins from here on: the best mutually distinct candidates over ALL blocks of the previous level
+            // (two candidates further apart than that level's window belong to different basins)
+            zp.first_level = 1;
+            zp.n_prev = n_prev * starts_prev;
+            zp.sep0 = 2.0 * h0 * ratio_prev;
+            zp.sep1 = 2.0 * h1 * ratio_prev;
+        } else {
+            zp.first_level = 0;
+            zp.n_prev = n_prev;
+        }
+        if (f32) search_zoom_kernel<METHOD, float><<<per_start * n_starts, SEARCH_THREADS, smem_zoom, st>>>(zp);
+        else search_zoom_kernel<METHOD, double><<<per_start * n_starts, SEARCH_THREADS, smem_zoom, st>>>(zp);
         e = cudaGetLastError();
         if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_zoom launch");
         n_prev = per_start * SEARCH_K;                 // candidates per start
+        starts_prev = n_starts;
         prev = cur;
         cur = (cur == listB) ? listA : listB;
-        h0 /= 5.0;
-        h1 /= 5.0;
+        ratio_prev = (lvl == 0) ? g_tuning.first_ratio : 5.0;
+        h0 /= ratio_prev;
+        h1 /= ratio_prev;
     }
-    search_finalize_kernel<<<1, SEARCH_THREADS, 0, st>>>(prev, n_prev * ZOOM_STARTS, result);
+    const int n_starts = starts_prev;
+    search_finalize_kernel<<<1, SEARCH_THREADS, 0, st>>>(prev, n_prev * n_starts, result);
     e = cudaGetLastError();
     if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_finalize launch");
     return XMR_OK;
@@ -139,6 +172,23 @@ int xmr_row_absmax_c64(const void* spec_dev, int64_t batch, int n, float* absmax
                                                                          absmax_dev, argmax_dev);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? XMR_OK : xmr_abi::cuda_fail(e, "row_absmax launch");
+}
+
+int xmr_autophase_search_tuning(double p0_step_deg, double p1_step_deg, int starts, int levels, int f32_levels,
+                                int late_starts, double first_ratio) {
+    if (!(p0_step_deg > 0.0) || !(p1_step_deg > 0.0) || p0_step_deg > 45.0 || p1_step_deg > 500.0 || starts < 1 ||
+        starts > ZOOM_MAX_STARTS || levels < 1 || levels > 12 || starts * ZOOM_SIDE * ZOOM_CHUNKS * SEARCH_K > WS_LIST ||
+        f32_levels < 0 || late_starts < 1 || !(first_ratio >= 1.0) || first_ratio > 10.0)
+        return xmr_abi::fail(XMR_ERR_BAD_ARG, "search tuning: p0_step=%g p1_step=%g starts=%d levels=%d f32_levels=%d "
+                             "late_starts=%d", p0_step_deg, p1_step_deg, starts, levels, f32_levels, late_starts);
+    g_tuning.f32_levels = f32_levels;
+    g_tuning.first_ratio = first_ratio;
+    g_tuning.late_starts = late_starts;
+    g_tuning.p0_step = p0_step_deg;
+    g_tuning.p1_step = p1_step_deg;
+    g_tuning.starts = starts;
+    g_tuning.levels = levels;
+    return XMR_OK;
 }
 
 int64_t xmr_autophase_workspace_bytes(void) { return int64_t(sizeof(Cand)) * 2 * WS_LIST; }

@@ -46,7 +46,6 @@ template <int METHOD>
 __global__ void __launch_bounds__(SEARCH_THREADS) search_coarse_kernel(const __grid_constant__ SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sp = reinterpret_cast<float2*>(smem_raw);
-    __shared__ Cand warp_best[SEARCH_THREADS / 32];
     const int n = p.n;
     const int L = (n + 31) / 32;
     const int padshift = ilog2_ceil(L);
@@ -81,13 +80,11 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_coarse_kernel(const __g
             if (double(f) < best_f) { best_f = double(f); best_p0 = p0k[k]; best_p1 = p1; }
         }
     }
-    if (lane == 0) { warp_best[warp].f = best_f; warp_best[warp].p0 = best_p0; warp_best[warp].p1 = best_p1; warp_best[warp].pad = 0; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        Cand b = warp_best[0];
-        for (int w = 1; w < SEARCH_THREADS / 32; ++w)
-            if (warp_best[w].f < b.f) b = warp_best[w];
-        p.out[blockIdx.x] = b;
+    // every warp reports its own best cell: the zoom stage picks several mutually distinct starts from this list
+    if (lane == 0) {
+        Cand b;
+        b.f = best_f; b.p0 = best_p0; b.p1 = best_p1; b.pad = 0;
+        p.out[blockIdx.x * (SEARCH_THREADS / 32) + warp] = b;
     }
 }
 
@@ -102,13 +99,14 @@ struct ZoomParams {
     double p0_lo, p0_hi, p1_lo, p1_hi;
     int rows;           // 21 (two parameters) or 1 (p0 only)
     Cand* cur;          // n_starts * rows * 3 * SEARCH_K candidates (one contiguous block per start)
-    int n_starts;       // basins refined in parallel (ZOOM_STARTS)
-    int first_level;    // 1: prev is the coarse list shared by all starts (start s takes the s-th best DISTINCT cell);
+    int n_starts;       // basins refined in parallel (<= ZOOM_MAX_STARTS)
+    int first_level;    // 1: prev is ONE list of n_prev candidates shared by all starts (start s takes the s-th best
+                        //    DISTINCT one): the coarse grid's list, or all blocks of a level that ran more starts;
                         // 0: prev holds one block of n_prev candidates per start
     double sep0, sep1;  // first level: two cells are distinct when they differ by more than this in p0 or in p1
 };
 
-constexpr int ZOOM_STARTS = 2;  // the two best distinct coarse cells are refined side by side (one wave of 126 CTAs)
+constexpr int ZOOM_MAX_STARTS = 8;  // the best distinct coarse cells are refined side by side (63 CTAs each)
 constexpr int ZOOM_SIDE = 21;   // 21 x 21 points per level, spacing h/10
 constexpr int ZOOM_CHUNKS = 3;  // 3 * SEARCH_K = 24 >= 21
 
@@ -118,10 +116,10 @@ __device__ __forceinline__ bool cand_distinct(const Cand& a, const Cand& b, doub
     return d0 > sep0 || fabs(a.p1 - b.p1) > sep1;
 }
 
-// block-wide argmin of a candidate list (lowest index wins ties) -> broadcast.  `excl` (optional): skip candidates that
-// are not distinct from it.
-__device__ __forceinline__ Cand block_argmin(const Cand* list, int n_list, const Cand* excl = nullptr, double sep0 = 0.0,
-                                             double sep1 = 0.0) {
+// block-wide argmin of a candidate list (lowest index wins ties) -> broadcast.  Candidates that are not distinct from
+// every one of the `n_excl` cells in `excl` are skipped.
+__device__ __forceinline__ Cand block_argmin(const Cand* list, int n_list, const Cand* excl = nullptr, int n_excl = 0,
+                                             double sep0 = 0.0, double sep1 = 0.0) {
     __shared__ double sf[SEARCH_THREADS / 32];
     __shared__ int si[SEARCH_THREADS / 32];
     __shared__ int s_best;
@@ -129,7 +127,9 @@ __device__ __forceinline__ Cand block_argmin(const Cand* list, int n_list, const
     int idx = 0x7fffffff;
     for (int i = threadIdx.x; i < n_list; i += blockDim.x) {
         const double v = list[i].f;
-        if (excl != nullptr && !cand_distinct(list[i], *excl, sep0, sep1)) continue;
+        bool ok = true;
+        for (int e = 0; e < n_excl; ++e) ok = ok && cand_distinct(list[i], excl[e], sep0, sep1);
+        if (!ok) continue;
         if (v < f || (v == f && i < idx)) { f = v; idx = i; }
     }
 #pragma unroll
@@ -143,7 +143,7 @@ __device__ __forceinline__ Cand block_argmin(const Cand* list, int n_list, const
     if (threadIdx.x == 0) {
         for (int w = 1; w < int(blockDim.x >> 5); ++w)
             if (sf[w] < f || (sf[w] == f && si[w] < idx)) { f = sf[w]; idx = si[w]; }
-        s_best = (idx == 0x7fffffff) ? -1 : idx;
+        s_best = (idx == 0x7fffffff || !(f < CUDART_INF)) ? -1 : idx;
     }
     __syncthreads();
     const int b = s_best;
@@ -156,8 +156,10 @@ __device__ __forceinline__ Cand block_argmin(const Cand* list, int n_list, const
     return list[b];
 }
 
-// ---- zoom level: one CTA per (p1 row, chunk of K p0 values), float64, the 8 warps split the spectrum ---------
-template <int METHOD>
+// ---- zoom level: one CTA per (p1 row, chunk of K p0 values), the 8 warps split the spectrum -----------------------
+// R = float for the wide early levels (spacing >= 0.1 deg: objective differences between neighbouring candidates are far
+// above float32 summation noise), double for the final ones.  Per-warp partial sums are combined and scored in double.
+template <int METHOD, typename R>
 __global__ void __launch_bounds__(SEARCH_THREADS) search_zoom_kernel(const __grid_constant__ ZoomParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sp = reinterpret_cast<float2*>(smem_raw);
@@ -172,10 +174,11 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_zoom_kernel(const __gri
     const int start = blockIdx.x / per_start, local = blockIdx.x % per_start;
     Cand centre;                                          // (block_argmin contains the barriers that also publish `sp`)
     if (p.first_level) {
+        Cand chosen[ZOOM_MAX_STARTS];
         centre = block_argmin(p.prev, p.n_prev);
-        for (int s = 1; s <= start; ++s) {                // the (start+1)-th best cell that is distinct from the best one
-            const Cand first = centre;
-            centre = block_argmin(p.prev, p.n_prev, &first, p.sep0, p.sep1);
+        for (int s = 1; s <= start; ++s) {                // the (start+1)-th best cell, distinct from all better starts
+            chosen[s - 1] = centre;
+            centre = block_argmin(p.prev, p.n_prev, chosen, s, p.sep0, p.sep1);
         }
     } else {
         centre = block_argmin(p.prev + (size_t)start * p.n_prev, p.n_prev);
@@ -186,7 +189,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_zoom_kernel(const __gri
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double p1 = (p.rows == 1) ? centre.p1
                                     : fmin(fmax(centre.p1 + (row - ZOOM_SIDE / 2) * (p.h1 / (ZOOM_SIDE / 2)), p.p1_lo), p.p1_hi);
-    double c0[SEARCH_K], s0[SEARCH_K], p0k[SEARCH_K];
+    R c0[SEARCH_K], s0[SEARCH_K];
+    double p0k[SEARCH_K];
 #pragma unroll
     for (int k = 0; k < SEARCH_K; ++k) {
         const int i = min(ch * SEARCH_K + k, ZOOM_SIDE - 1);
@@ -194,19 +198,19 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_zoom_kernel(const __gri
         double q0 = centre.p0 + (i - ZOOM_SIDE / 2) * (p.h0 / (ZOOM_SIDE / 2));
         q0 = q0 > p.p0_hi ? q0 - 360.0 : (q0 < p.p0_lo ? q0 + 360.0 : q0);
         p0k[k] = q0;
-        sincospi(p0k[k] / 180.0, &s0[k], &c0[k]);
+        RealOps<R>::sincospi2(R(p0k[k] / 360.0), &s0[k], &c0[k]);
     }
     const int w0 = min(warp * per_warp, n), w1 = min(w0 + per_warp, n);
     const int m0 = min(w0 + (lane << padshift), w1), m1 = min(m0 + (1 << padshift), w1);
-    Acc<double, METHOD, SEARCH_K> acc;
+    Acc<R, METHOD, SEARCH_K> acc;
     acc.init();
-    lane_accumulate_rt<double, METHOD, SEARCH_K>(sp, padshift, m0, m1, p.geom, p1 / 360.0, p.u0, p.du, c0, s0, acc);
+    lane_accumulate_rt<R, METHOD, SEARCH_K>(sp, padshift, m0, m1, p.geom, R(p1 / 360.0), R(p.u0), R(p.du), c0, s0, acc);
     acc.warp_reduce();
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < SEARCH_K; ++k)
 #pragma unroll
-            for (int s = 0; s < 4; ++s) part[warp][k][s] = acc.a[k][s];
+            for (int s = 0; s < 4; ++s) part[warp][k][s] = double(acc.a[k][s]);
     }
     __syncthreads();
     if (threadIdx.x < SEARCH_K) {
