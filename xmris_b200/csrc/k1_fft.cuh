@@ -36,6 +36,7 @@ struct K1Params {
     double ph_a_turns;     // uniform phase: turns(m) = a + b*m
     double ph_b_turns;
     float2 ph_step[16];    // exp(2 pi i * b * R0*R1 * d), d < 16
+    float2 ph_fold[16];    // folded-phase variants: exp(2 pi i (a + b * ((R0*R1*d + N/2) mod N))), d < 16
     float* run_max2;       // k1_max_kernel: running global max of |S|^2 (device scalar, zeroed by the launcher)
 };
 
@@ -83,6 +84,12 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
     constexpr bool F = (FAST != 0);
     constexpr bool TW_PERSIST = (N <= 4096);
     constexpr int NTW = (C::R0 > 1) ? C::C0 * (C::R0 - 1) : 1;
+    constexpr bool TW1_TAB_ = (K1Smem<N>::TW1 != 0);
+    // Folded phase (fast store+phase variants): with the stored index m = k1 + R0*c + m0(d), m0(d) = (R0*R1*d + N/2) mod N,
+    // the rotation exp(2 pi i (a + b*m)) factors into E1(k1) * E2(c) * step(d).  E1 rides on the persistent stage-0
+    // twiddles, E2 on the shared stage-1 twiddle table (both are 1 at index 0, where no multiply exists), so the epilogue
+    // is ONE complex multiply per point by a kernel-parameter constant instead of two.
+    constexpr bool FOLD = F && ((FAST & K1_FAST_PHASE) != 0) && TW_PERSIST && TW1_TAB_ && C::R0 > 1;
     constexpr bool IPB = K1Smem<N>::INPLACE_B;
     constexpr int STAGES = K1Smem<N>::STAGES;
     constexpr size_t SLOT = K1Smem<N>::SLOT;
@@ -119,10 +126,25 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
 #pragma unroll
         for (int j = 0; j < C::C0; ++j) wcol[j] = p.win ? p.win[t + C::T * j] : p.scale;   // null: scale only
     }
+    if (FOLD) {
+#pragma unroll
+        for (int k1 = 1; k1 < C::R0; ++k1) {
+            double turns = p.ph_b_turns * double(k1);
+            turns -= floor(turns);
+            double s, c;
+            sincospi(2.0 * turns, &s, &c);
+#pragma unroll
+            for (int j = 0; j < C::C0; ++j) {
+                float2& w = tw_persist[(TW_PERSIST ? j * (C::R0 - 1) + k1 - 1 : 0)];
+                const double wr = double(w.x) * c - double(w.y) * s, wi = double(w.x) * s + double(w.y) * c;
+                w = make_float2(float(wr), float(wi));
+            }
+        }
+    }
     float2 ph_base[C::C2];
 #pragma unroll
     for (int j = 0; j < C::C2; ++j) ph_base[j] = make_float2(1.f, 0.f);
-    if (do_phase) {
+    if (do_phase && !FOLD) {
 #pragma unroll
         for (int j = 0; j < C::C2; ++j) {
             const int q = t + C::T * j;
@@ -154,6 +176,13 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
             const int c = i / 16 + 1, b = i % 16;
             float2 w = p.twN[(b * c * C::R0) % C::N];
             if (INVERSE) w.y = -w.y;
+            if (FOLD) {
+                double turns = p.ph_b_turns * double(C::R0 * c);
+                turns -= floor(turns);
+                double sn, cs;
+                sincospi(2.0 * turns, &sn, &cs);
+                w = make_float2(float(double(w.x) * cs - double(w.y) * sn), float(double(w.x) * sn + double(w.y) * cs));
+            }
             tw1_tab[i] = w;
         }
     }
@@ -285,7 +314,9 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
                     const int k = t + C::T * j + Q * d;
                     const int m = (k + out_shift) & (C::N - 1);
                     float2 x = v[j * C::R2 + d];
-                    if (do_phase) {
+                    if (FOLD) {
+                        x = cmul(x, p.ph_fold[d]);
+                    } else if (do_phase) {
                         // m = q + Q*d' with d' = m / Q: rot = base(q) * step(d')
                         const float2 r = cmul(ph_base[j], p.ph_step[(m / Q) & 15]);
                         x = cmul(x, r);

@@ -249,6 +249,11 @@ static int k1_dispatch(const void* fid_dev, void* spec_dev, int64_t batch, int n
         double turns = ph_b_turns * double(q) * double(d);
         turns -= std::floor(turns);
         p.ph_step[d] = make_float2(float(std::cos(2.0 * M_PI * turns)), float(std::sin(2.0 * M_PI * turns)));
+        // folded-phase fast variants (out_shift = n_out/2): the whole rotation of stored index m0(d) = (q*d + N/2) mod N
+        const long long m0 = (static_cast<long long>(q) * d + n_out / 2) % n_out;
+        double tf = ph_a_turns + ph_b_turns * double(m0);
+        tf -= std::floor(tf);
+        p.ph_fold[d] = make_float2(float(std::cos(2.0 * M_PI * tf)), float(std::sin(2.0 * M_PI * tf)));
     }
     // TMA bulk copies need 16-byte aligned rows
     const bool tma = ((reinterpret_cast<uintptr_t>(fid_dev) & 15) == 0) && ((n_in & 1) == 0);
