@@ -186,3 +186,54 @@ def test_arbitrary_length_chirp_z(dev, n_in, n_out):
     back, _, _ = D.fid_to_spectrum(spec, inverse=True, in_shift=n_out // 2, out_shift=0)
     ref_back, _ = orc.to_fid(ref, 1, freqs)
     assert rel_l2(back.cpu().numpy(), ref_back) < TOL
+
+
+# ---- pass 1 of mode="single": branch-and-bound statistics must pick exactly the plain pass's winner --------------------
+def _pruned_vs_plain(dev, fid_np, window):
+    import torch
+
+    from xmris_b200 import device as D
+
+    fid = torch.from_numpy(np.ascontiguousarray(fid_np.astype(np.complex64))).to(dev)
+    n = fid.shape[-1]
+    pruned, running = D.fid_absmax_pruned(fid, n_out=n, window=window)
+    _, plain, _ = D.fid_to_spectrum(fid, n_out=n, window=window, store=False, want_stats=True, want_index=False)
+    vp, ip = D.global_argmax(pruned.reshape(-1), None, n)
+    vq, iq = D.global_argmax(plain.reshape(-1), None, n)
+    pruned, plain = pruned.cpu().numpy(), plain.cpu().numpy()
+    kept = pruned > 0
+    assert ip == iq, "branch and bound changed the winning row"
+    assert vp == vq
+    assert np.allclose(pruned[kept], plain[kept], rtol=1e-6, atol=0)
+    assert np.all(plain[~kept] <= vq)                       # pruned rows could not have won
+    assert abs(float(running.item()) ** 0.5 - vq) <= 1e-6 * max(vq, 1e-30)
+    return kept.mean()
+
+
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096])
+def test_pruned_statistics_pick_the_exact_winner(dev, n):
+    from xmris_b200.synth import make_fids_numpy
+
+    rng = np.random.default_rng(n)
+    t = np.arange(n) / 5000.0
+    window = np.exp(-np.pi * 5.0 * t) / np.sqrt(n)
+    # (a) MRSI-like decaying multi-line FIDs (odd batch: a ragged last tile)
+    fid, _, _ = make_fids_numpy("1H", 3001, n, seed=n)
+    kept = _pruned_vs_plain(dev, fid, window)
+    assert kept < 0.9                                        # the bounds do prune on this kind of data
+    # (b) undamped single tones of ascending amplitude: every bound is tight, almost nothing can be pruned
+    k = rng.integers(0, n, size=257)
+    tones = (np.arange(1, 258)[:, None] * np.exp(2j * np.pi * k[:, None] * np.arange(n)[None, :] / n))
+    _pruned_vs_plain(dev, tones, None)
+    # (c) identical rows: ties resolve to the first row (numpy argmax order, phasing.py:229-231)
+    same = np.repeat(fid[:1], 300, axis=0)
+    _pruned_vs_plain(dev, same, window)
+    # (d) zeros, one impulse row, noise rows
+    mixed = np.zeros((65, n), dtype=np.complex128)
+    mixed[17, 3] = 5.0
+    mixed[40:] = rng.standard_normal((25, n)) + 1j * rng.standard_normal((25, n))
+    _pruned_vs_plain(dev, mixed, None)
+    _pruned_vs_plain(dev, np.zeros((9, n), dtype=np.complex128), window)
+    # (e) separable windows with negative factors (the level-0 bound uses |w|)
+    _pruned_vs_plain(dev, fid[:500], -window)
+    _pruned_vs_plain(dev, fid[:500], window * np.where((np.arange(n) // min(n, 256)) % 2 == 1, -1.0, 1.0))
