@@ -12,7 +12,7 @@ matplotlib / pyAMARES, and xarray itself is not installed).  We therefore
   2. pre-seed ``sys.modules["xmris"]`` with an empty namespace package whose ``__path__`` points at
      ``/root/reference/src/xmris`` (this skips ``xmris/__init__.py``),
   3. import ``xmris.core.config``, ``xmris.core.utils``, ``xmris.processing.fourier``,
-     ``xmris.processing.fid`` and ``xmris.processing.phasing`` from the read-only tree.
+     ``xmris.processing.fid``, ``xmris.processing.phasing`` and ``xmris.vendor.bruker`` from the read-only tree.
 Numeric results depend only on numpy/scipy; the stand-in affects metadata plumbing only.
 No reference source is copied into this repository.
 """
@@ -64,6 +64,7 @@ def load_reference():
     _pkg("xmris", REFERENCE_SRC)
     _pkg("xmris.core", os.path.join(REFERENCE_SRC, "core"))
     _pkg("xmris.processing", os.path.join(REFERENCE_SRC, "processing"))
+    _pkg("xmris.vendor", os.path.join(REFERENCE_SRC, "vendor"))
 
     ns = types.SimpleNamespace()
     ns.xr = xr
@@ -72,5 +73,6 @@ def load_reference():
     ns.fourier = importlib.import_module("xmris.processing.fourier")
     ns.fid = importlib.import_module("xmris.processing.fid")
     ns.phasing = importlib.import_module("xmris.processing.phasing")
+    ns.bruker = importlib.import_module("xmris.vendor.bruker")      # remove_digital_filter ("next" row N4)
     _loaded = ns
     return ns

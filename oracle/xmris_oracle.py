@@ -326,6 +326,44 @@ def autophase_each(values, axis, coord, method="acme", peak_width=0.5, target_co
 
 
 # --------------------------------------------------------------------------------------------
+# N4  remove_digital_filter                              reference: vendor/bruker.py:7-118
+# --------------------------------------------------------------------------------------------
+
+
+def remove_digital_filter(values, axis, coord, group_delay, keep_length=True):
+    """Bruker group-delay removal: drop ``floor(gd)`` points, shift the rest by the fractional part with an
+    FFT phase ramp, optionally pad zeros back to the original length (``vendor/bruker.py:55-118``).
+
+    Returns ``(values, coord)``; ``group_delay <= 0`` returns copies (``bruker.py:58-59``)."""
+    values = np.asarray(values)
+    coord = np.asarray(coord, dtype=np.float64)
+    if group_delay <= 0:
+        return values.copy(), coord.copy()
+    int_delay = int(np.floor(group_delay))                                   # bruker.py:62-63
+    frac_delay = group_delay - int_delay
+    sl = [slice(None)] * values.ndim
+    sl[axis] = slice(int_delay, None)
+    cut = values[tuple(sl)] if int_delay > 0 else values                      # bruker.py:67-70
+    cut_coord = coord[int_delay:] if int_delay > 0 else coord
+    if not np.isclose(frac_delay, 0.0):                                       # bruker.py:73-87
+        n_points = cut.shape[axis]
+        freqs = _bcast(np.fft.fftfreq(n_points), cut.ndim, axis)
+        spectrum = np.fft.fft(cut, axis=axis)
+        corrected = np.fft.ifft(spectrum * np.exp(1j * 2 * np.pi * freqs * frac_delay), axis=axis)
+    else:
+        corrected = cut
+    if int_delay > 0 and keep_length:                                         # bruker.py:92-99
+        pad_shape = list(corrected.shape)
+        pad_shape[axis] = int_delay
+        final = np.concatenate((corrected, np.zeros(pad_shape, dtype=corrected.dtype)), axis=axis)
+        new_coord = coord
+    else:
+        final = corrected
+        new_coord = cut_coord
+    return final, new_coord - new_coord[0]                                    # bruker.py:107-108
+
+
+# --------------------------------------------------------------------------------------------
 # The chain                                                            README.md:66-73
 # --------------------------------------------------------------------------------------------
 

@@ -156,3 +156,45 @@ def test_autophase_each_is_loop_of_single():
     for i, c in enumerate(cases):
         assert (p0[i], p1[i], piv[i]) == (c["p0"], c["p1"], c["pivot"])
         np.testing.assert_array_equal(out[i], c["phased"])
+
+
+# ---- "next" row N4: remove_digital_filter (vendor/bruker.py:7-118), tests/golden/make_golden_bruker.py ---------------
+
+
+def _bruker_block():
+    """The seeded synthetic input of make_golden_bruker.py (regenerated, not stored)."""
+    rng = np.random.default_rng(2026)
+    n, sw = 1024, 5000.0
+    t = np.arange(n) / sw
+    base = np.exp((-20.0 + 2j * np.pi * 333.0) * t)
+    blk = np.stack([np.stack([np.roll(base, 76) * (1 + c) + 0.01 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+                              for c in range(2)], axis=-1) for _ in range(2)], axis=0)
+    return blk, t
+
+
+@pytest.mark.parametrize("tag", list("abcdef"))
+def test_remove_digital_filter_matches_reference_bitwise(tag):
+    g = load_golden("bruker")
+    blk, t = _bruker_block()
+    out, coord = orc.remove_digital_filter(blk, 1, t, float(g[f"syn_{tag}_gd"]), bool(g[f"syn_{tag}_keep"]))
+    want = g[f"syn_{tag}_out"] if f"syn_{tag}_out" in g else blk            # gd <= 0: a plain copy (bruker.py:58-59)
+    assert out.shape == want.shape and np.array_equal(out, want)
+    assert np.array_equal(coord, g[f"syn_{tag}_time"])
+
+
+def test_bruker_fixture_known_answer():
+    """The reference's real 1H fixture (tests/data/nspect_slab_1H): group delay 76.125 -> 1972 points -> spectrum; the
+    water line sits within one bin of the fixture's ground truth (-2.58 Hz / 4.680 ppm, ground_truth.toml:16)."""
+    g = load_golden("bruker")
+    one = g["real_fid"][:, 0]
+    clean, tt = orc.remove_digital_filter(one, 0, g["real_time"], float(g["real_gd"]), keep_length=False)
+    assert clean.shape == (1972,) and np.array_equal(clean, g["real_clean"]) and np.array_equal(tt, g["real_clean_time"])
+    spec, freq = orc.to_spectrum(clean, 0, tt)
+    assert np.array_equal(spec, g["real_spectrum"]) and np.array_equal(freq, g["real_freq"])
+    peak_hz = freq[int(np.argmax(np.abs(spec)))]
+    df = freq[1] - freq[0]
+    assert abs(peak_hz - float(g["truth_hz"])) <= df
+    ppm = float(g["real_carrier"]) + peak_hz / float(g["real_f0"])
+    assert abs(ppm - float(g["truth_ppm"])) <= df / float(g["real_f0"])
+    allc, _ = orc.remove_digital_filter(g["real_fid"], 0, g["real_time"], float(g["real_gd"]), keep_length=True)
+    assert np.array_equal(allc, g["real_all_clean"])

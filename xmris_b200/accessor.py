@@ -1,7 +1,8 @@
 """The ``.xmr`` accessor for the hot path -- drop-in for the reference's ``XmrisAccessor`` methods
 ``zero_fill`` / ``apodize_exp`` / ``to_spectrum`` / ``phase`` / ``autophase`` (``src/xmris/core/accessor.py:452-683``),
 same names, argument order and defaults (checked by the reference's ``tests/test_core.py:509-552``), plus the "next"
-rows ``to_fid`` / ``apodize_lg`` and the fused entry point ``process_fid``.
+rows ``to_fid`` / ``apodize_lg`` / ``to_ppm`` / ``to_hz`` / ``remove_digital_filter`` and the fused entry point
+``process_fid``.
 
 Registered on the bundled ``xarray_lite.DataArray`` always, and on real ``xarray.DataArray`` when xarray imports
 (registering under ``"xmr"`` overrides the reference's accessor if both packages are imported).
@@ -71,6 +72,10 @@ class XmrisB200Accessor:
         # phasing.py:166); mode / target_coord / p0_only travel in **kwargs (accessor.py:637, 682).
         return P.autophase(self._obj, dim=dim, method=method, peak_width=peak_width, lb=lb,
                            temp_time_dim=temp_time_dim, **kwargs)
+
+    # --- vendor specific (accessor.py:829-859) ---
+    def remove_digital_filter(self, group_delay: float, dim: str = "time", keep_length: bool = True):
+        return P.remove_digital_filter(self._obj, group_delay=group_delay, dim=dim, keep_length=keep_length)
 
     # --- fused chain (B200 extension) ---
     def process_fid(self, dim: str = DIMS.time, out_dim: str = DIMS.frequency, target_points: int | None = None,

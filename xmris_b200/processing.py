@@ -366,6 +366,52 @@ def to_hz(da, dim: str = DIMS.chemical_shift):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# N4 remove_digital_filter                                          reference: vendor/bruker.py:7-118
+# ---------------------------------------------------------------------------------------------------------
+
+
+def remove_digital_filter(da, group_delay: float, dim: str = "time", keep_length: bool = True):
+    """Remove the Bruker digital-filter group delay (``vendor/bruker.py:7-118``): drop ``floor(group_delay)`` leading
+    points, shift the rest by the fractional part (FFT, phase ramp ``exp(2 pi i f frac)``, inverse FFT -- on the
+    device; lengths that are not powers of two, e.g. 2048 - 76 = 1972, run through the chirp-z composition) and, with
+    ``keep_length``, pad zeros at the end back to the original length.  Time coordinate restarts at 0; lineage attrs
+    as in the reference."""
+    if dim not in da.dims:
+        raise ValueError(f"Dimension '{dim}' missing in DataArray.")
+    if group_delay <= 0:
+        return da.copy()
+    int_delay = int(np.floor(group_delay))
+    frac_delay = group_delay - int_delay
+    axis = da.get_axis_num(dim)
+    cut = da.isel({dim: slice(int_delay, None)}) if int_delay > 0 else da
+    n_points = cut.sizes[dim]
+    padded = int_delay > 0 and keep_length
+    template = da if padded else cut
+    if not np.isclose(frac_delay, 0.0):
+        x = _to_device(cut.values, axis)
+        spec, _, _ = D.fid_to_spectrum(x, n_out=n_points, scale=1.0, out_shift=0)                    # np.fft.fft
+        spec = D.rotate_rows(spec, np.exp(1j * 2 * np.pi * np.fft.fftfreq(n_points) * frac_delay))   # bruker.py:84
+        back, _, _ = D.fid_to_spectrum(spec, inverse=True, scale=1.0 / n_points, in_shift=0, out_shift=0)
+        if padded:
+            back = D.zero_fill(back, da.sizes[dim], 0)
+        values = _from_device(back, axis)
+    else:
+        # whole-sample delay: pure data movement, the reference touches no value (bruker.py:88-89)
+        values = np.asarray(cut.values)
+        if padded:
+            shape = list(values.shape)
+            shape[axis] = int_delay
+            values = np.concatenate((values, np.zeros(shape, dtype=values.dtype)), axis=axis)
+    res = template.copy(data=values)
+    t = np.asarray(res.coords[dim].values)
+    res = res.assign_coords({dim: t - t[0]})
+    attrs = dict(da.attrs)
+    attrs.update({"digital_filter_removed": True, "group_delay_removed": group_delay,
+                  "length_retained_with_zeros": keep_length})
+    return res.assign_attrs(attrs)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # A4 phase                                                          reference: processing/phasing.py:10-96
 # ---------------------------------------------------------------------------------------------------------
 
