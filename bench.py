@@ -208,6 +208,28 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------------------
 
 
+def bind_host_to_gpu(torch, local_rank):
+    """Multi-GPU runs: restrict this rank's host threads to the CPUs NVML reports as local to its GPU, so that the pinned
+    e2e buffers are first-touched on that GPU's NUMA node.  Returns the CPU list used (None: left unchanged)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        local = {i * 64 + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = local & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            return sorted(use)
+    except Exception:   # no NVML / no affinity information: leave the scheduler alone
+        pass
+    return None
+
+
+
 def run_ours(args):
     import torch
 
@@ -226,6 +248,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_cpus = bind_host_to_gpu(torch, local_rank) if world > 1 else None
     batch, n = args.batch, N_POINTS
     t = time_coord(n, 5000.0)
 
@@ -261,7 +284,7 @@ def run_ours(args):
                 e1.record()
                 k2_ms.append((e0, e1))
                 parts.append((ea, e0, e1))
-            launches["n"] += 13   # K1 stats, argmax x2, K1 (1 row), coarse, 6 zoom, finalize, K1 store+phase
+            launches["n"] += 11   # K1-max, argmax x2, K1 (1 row), coarse, 4 zoom, finalize, K1 store+phase
             return p0, p1, pivot
         from xmris_b200 import pervoxel
 
@@ -359,6 +382,31 @@ def run_ours(args):
         e2e = {"value": world * eb / dt, "unit": "spectra/s", "h2d_bytes_per_step": int(eb * n * 8),
                "d2h_bytes_per_step": int(eb * n * 8), "voxels_per_gpu": eb, "ms_per_step": dt * 1e3,
                "api": "hostpipe.HostChain.run_many: pinned host batches, H2D of batch i+1 overlaps D2H of batch i"}
+        if host_cpus is not None:
+            e2e["host_cpus_bound_to_gpu"] = len(host_cpus)
+
+        # the PCIe ceiling this leg runs against: the same pinned buffers copied with nothing else going on
+        # (one direction at a time, then both at once), every rank at the same time
+        def copy_rate(h2d, d2h):
+            sa, sb = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            barrier()
+            t1 = time.perf_counter()
+            for _ in range(2):
+                if h2d:
+                    with torch.cuda.stream(sa):
+                        pipe.d_ins[0].copy_(h_in, non_blocking=True)
+                if d2h:
+                    with torch.cuda.stream(sb):
+                        h_out.copy_(pipe.d_ins[1], non_blocking=True)
+            sa.synchronize()
+            sb.synchronize()
+            return 2 * eb * n * 8 / (time.perf_counter() - t1) / 1e9
+
+        up, down, both = copy_rate(True, False), copy_rate(False, True), copy_rate(True, True)
+        e2e["pcie"] = {"h2d_gbs": up, "d2h_gbs": down, "duplex_each_way_gbs": both,
+                       "what": "plain pinned copies of the same buffers, GB/s per direction (rank 0%s)"
+                               % ("" if dist is None else ", all ranks copying at once")}
+        e2e["frac_of_pcie_duplex"] = (eb * n * 8 / dt / 1e9) / both
 
         # the same chain through ONE C-ABI call on the same pinned host buffers (numpy view, no torch on the path)
         if dist is None:
