@@ -36,6 +36,67 @@ def test_accessor_defaults_match_reference():
     assert COORDS.chemical_shift.long_name == "Chemical Shift" and ATTRS.phase_pivot_coord == "phase_pivot_coord"
 
 
+def test_reference_dim_defaults_table():
+    # every (method, parameter, default) row of the reference's tests/test_core.py:509-530 that is on or beside the path
+    rows = [("fft", "dim", "time"), ("ifft", "dim", "frequency"), ("fftc", "dim", "time"), ("ifftc", "dim", "frequency"),
+            ("apodize_exp", "dim", "time"), ("apodize_lg", "dim", "time"), ("to_spectrum", "dim", "time"),
+            ("to_spectrum", "out_dim", "frequency"), ("to_fid", "dim", "frequency"), ("to_fid", "out_dim", "time"),
+            ("zero_fill", "dim", "time"), ("autophase", "dim", "frequency"), ("remove_digital_filter", "dim", "time"),
+            ("to_ppm", "dim", "frequency"), ("to_hz", "dim", "chemical_shift"), ("to_real_imag", "dim", "component"),
+            ("to_complex", "dim", "component")]
+    for method, param, want in rows:
+        assert inspect.signature(getattr(XmrisB200Accessor, method)).parameters[param].default == want, (method, param)
+    assert _defaults(XmrisB200Accessor.remove_digital_filter) == {"dim": "time", "keep_length": True}
+
+
+def test_real_imag_round_trip_known_answer():
+    # docs/notebooks/basics/complex_numbers.md:79-151 (the notebook's strict CI cell), host data re-labelling only
+    t = np.linspace(0, 1, 512)
+    fid = np.exp(-t * 3.0) * np.exp(1j * 2 * np.pi * 15.0 * t)
+    da = xr.DataArray(fid, dims=["time"], coords={"time": t}, attrs={"B0": 3.0}, name="Signal")
+    split = da.xmr.to_real_imag()
+    assert split.ndim == da.ndim + 1 and split.sizes["component"] == 2 and not np.iscomplexobj(split.values)
+    assert list(split.coords["component"].values) == ["real", "imag"] and split.dims == ("time", "component")
+    recon = split.xmr.to_complex()
+    assert recon.ndim == da.ndim and np.iscomplexobj(recon.values) and "component" not in recon.dims
+    np.testing.assert_array_equal(recon.values, da.values)
+    assert recon.attrs["B0"] == 3.0 and recon.name == "Signal" and split.attrs["B0"] == 3.0
+    np.testing.assert_array_equal(recon.coords["time"].values, t)
+    custom = da.xmr.to_real_imag(dim="channel", coords=("ch0", "ch1"))
+    assert custom.dims == ("time", "channel")
+    np.testing.assert_array_equal(custom.xmr.to_complex(dim="channel", coords=("ch0", "ch1")).values, fid)
+    # component axis in the middle (the layout of the reference's Bruker netCDF fixtures is (raw, component))
+    mid = xr.DataArray(np.arange(12.0).reshape(2, 2, 3), dims=["v", "component", "time"],
+                       coords={"component": ["real", "imag"], "time": [0.0, 0.1, 0.2]})
+    c = mid.xmr.to_complex()
+    assert c.dims == ("v", "time")
+    np.testing.assert_array_equal(c.values, mid.values[:, 0, :] + 1j * mid.values[:, 1, :])
+    with pytest.raises(ValueError, match="missing dimension"):
+        da.xmr.to_complex()
+
+
+def test_remove_digital_filter_host_branches():
+    # branches that never reach the device: missing dim, non-positive delay (copy), whole-sample delay (slice + zeros)
+    t = np.arange(32) / 1000.0
+    v = np.arange(64, dtype=float).reshape(2, 32) + 1j
+    da = xr.DataArray(v, dims=["rep", "time"], coords={"time": t}, attrs={"a": 1})
+    with pytest.raises(ValueError, match="Dimension 'nope' missing in DataArray."):
+        da.xmr.remove_digital_filter(3.0, dim="nope")
+    same = da.xmr.remove_digital_filter(0.0)
+    np.testing.assert_array_equal(same.values, v)
+    assert same.attrs == {"a": 1}
+    from oracle import xmris_oracle as orc
+
+    for keep in (True, False):
+        r = da.xmr.remove_digital_filter(5.0, keep_length=keep)
+        want, coord = orc.remove_digital_filter(v, 1, t, 5.0, keep)
+        np.testing.assert_array_equal(r.values, want)
+        np.testing.assert_array_equal(r.coords["time"].values, coord)
+        assert r.attrs == {"a": 1, "digital_filter_removed": True, "group_delay_removed": 5.0,
+                           "length_retained_with_zeros": keep}
+    np.testing.assert_array_equal(da.values, v)
+
+
 def test_check_dims_error_text():
     # reference tests/test_core.py:411-440
     da = xr.DataArray(np.zeros((2, 4)), dims=["voxel", "t"])

@@ -77,6 +77,13 @@ class XmrisB200Accessor:
     def remove_digital_filter(self, group_delay: float, dim: str = "time", keep_length: bool = True):
         return P.remove_digital_filter(self._obj, group_delay=group_delay, dim=dim, keep_length=keep_length)
 
+    # --- utility / formatting (accessor.py:863-878; host data re-labelling only) ---
+    def to_real_imag(self, dim: str = DIMS.component, coords: tuple = ("real", "imag")):
+        return P.to_real_imag(self._obj, dim=dim, coords=coords)
+
+    def to_complex(self, dim: str = DIMS.component, coords: tuple = ("real", "imag")):
+        return P.to_complex(self._obj, dim=dim, coords=coords)
+
     # --- fused chain (B200 extension) ---
     def process_fid(self, dim: str = DIMS.time, out_dim: str = DIMS.frequency, target_points: int | None = None,
                     position: str = "end", lb: float | None = None, autophase_kwargs: dict | None = None):

@@ -366,6 +366,37 @@ def to_hz(da, dim: str = DIMS.chemical_shift):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# data formats either side of the path                               reference: processing/utils.py:8-84
+# ---------------------------------------------------------------------------------------------------------
+# Storage formats without complex numbers (netCDF: the reference's Bruker fixtures) keep (real, imag) along a
+# ``component`` dimension.  Pure re-labelling of host data: no arithmetic, nothing for the device to do.
+
+
+def to_real_imag(da, dim: str = DIMS.component, coords: tuple = ("real", "imag")):
+    """Complex array -> real array with a trailing ``dim`` of size 2 (``processing/utils.py:8-41``)."""
+    values = np.asarray(da.values)
+    new = xr.DataArray(np.stack([values.real, values.imag], axis=-1), dims=tuple(da.dims) + (dim,),
+                       coords={**{k: da.coords[k] for k in da.coords}, dim: list(coords)}, name=da.name)
+    return new.assign_attrs(da.attrs)
+
+
+def to_complex(da, dim: str = DIMS.component, coords: tuple = ("real", "imag")):
+    """(real, imag) along ``dim`` -> complex array without ``dim`` (``processing/utils.py:44-84``)."""
+    _check_dims(da, dim, "to_complex")
+    labels = list(np.asarray(da.coords[dim].values))          # KeyError for a bare dimension, like ``.sel``
+    try:
+        i_re, i_im = labels.index(coords[0]), labels.index(coords[1])
+    except ValueError as exc:
+        raise KeyError(f"not all values found in index {dim!r}: {exc}") from exc
+    axis = da.get_axis_num(dim)
+    values = np.asarray(da.values)
+    merged = np.take(values, i_re, axis=axis) + 1j * np.take(values, i_im, axis=axis)
+    res = xr.DataArray(merged, dims=tuple(d for d in da.dims if d != dim),
+                       coords={k: da.coords[k] for k in da.coords if dim not in da.coords[k].dims}, name=da.name)
+    return res.assign_attrs(da.attrs)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # N4 remove_digital_filter                                          reference: vendor/bruker.py:7-118
 # ---------------------------------------------------------------------------------------------------------
 

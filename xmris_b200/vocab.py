@@ -38,6 +38,7 @@ class _Dims:
     time = XmrisTerm("time", "Time-domain dimension for Free Induction Decay (FID) data.")
     frequency = XmrisTerm("frequency", "Frequency-domain dimension.")
     chemical_shift = XmrisTerm("chemical_shift", "Chemical shift dimension.")
+    component = XmrisTerm("component", "Dimension separating real and imaginary parts.")
 
 
 class _Coords:
