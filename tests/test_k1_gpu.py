@@ -189,15 +189,16 @@ def test_arbitrary_length_chirp_z(dev, n_in, n_out):
 
 
 # ---- pass 1 of mode="single": branch-and-bound statistics must pick exactly the plain pass's winner --------------------
-def _pruned_vs_plain(dev, fid_np, window):
+def _pruned_vs_plain(dev, fid_np, window, n_out=None, pad_left=0):
     import torch
 
     from xmris_b200 import device as D
 
     fid = torch.from_numpy(np.ascontiguousarray(fid_np.astype(np.complex64))).to(dev)
-    n = fid.shape[-1]
-    pruned, running = D.fid_absmax_pruned(fid, n_out=n, window=window)
-    _, plain, _ = D.fid_to_spectrum(fid, n_out=n, window=window, store=False, want_stats=True, want_index=False)
+    n = fid.shape[-1] if n_out is None else n_out
+    pruned, running = D.fid_absmax_pruned(fid, n_out=n, pad_left=pad_left, window=window)
+    _, plain, _ = D.fid_to_spectrum(fid, n_out=n, pad_left=pad_left, window=window, store=False, want_stats=True,
+                                    want_index=False)
     vp, ip = D.global_argmax(pruned.reshape(-1), None, n)
     vq, iq = D.global_argmax(plain.reshape(-1), None, n)
     pruned, plain = pruned.cpu().numpy(), plain.cpu().numpy()
@@ -237,3 +238,24 @@ def test_pruned_statistics_pick_the_exact_winner(dev, n):
     # (e) separable windows with negative factors (the level-0 bound uses |w|)
     _pruned_vs_plain(dev, fid[:500], -window)
     _pruned_vs_plain(dev, fid[:500], window * np.where((np.arange(n) // min(n, 256)) % 2 == 1, -1.0, 1.0))
+
+
+@pytest.mark.parametrize("n_in,n_out,pad_left,table", [(4096, 8192, 0, False), (8192, 8192, 0, False), (1024, 2048, 0, False),
+                                                       (1024, 4096, 1536, False), (2048, 2048, 0, True), (100, 256, 0, False),
+                                                       (64, 64, 0, False), (1000, 4096, 7, True)])
+def test_pruned_statistics_any_geometry(dev, n_in, n_out, pad_left, table):
+    """Zero-filled / long / short transforms and non-separable windows prune on the level-0 bound inside the generic
+    statistics kernel: same winner as the plain pass."""
+    from xmris_b200.synth import make_fids_numpy
+
+    fid, _, _ = make_fids_numpy("1H", 1501, n_in, seed=n_in + n_out)
+    t = (np.arange(n_out) - pad_left) / 5000.0
+    window = np.exp(-np.pi * 5.0 * np.abs(t)) / np.sqrt(n_out)
+    if table:
+        window = window * (1.0 + 0.3 * np.cos(np.arange(n_out) * 0.37))         # does not factor into rows x columns
+    kept = _pruned_vs_plain(dev, fid, window, n_out=n_out, pad_left=pad_left)
+    if n_in >= 1024:
+        assert kept < 0.9
+    same = np.repeat(fid[:1], 70, axis=0)
+    _pruned_vs_plain(dev, same, window, n_out=n_out, pad_left=pad_left)
+    _pruned_vs_plain(dev, np.zeros((5, n_in), dtype=np.complex128), window, n_out=n_out, pad_left=pad_left)

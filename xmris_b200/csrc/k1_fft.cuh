@@ -78,8 +78,13 @@ __device__ __forceinline__ void amax_combine(float& v, int& i, float ov, int oi)
 //            fixed at compile time (bit mask of K1_FAST_*): no per-element predicates or index arithmetic.
 enum : int { K1_FAST_ON = 1, K1_FAST_STORE = 2, K1_FAST_STATS = 4, K1_FAST_PHASE = 8 };
 
-template <int N, bool INVERSE, int WIN, bool TMA, int FAST = 0>
+// PRUNE (generic statistics-only launches with p.run_max2 set): branch and bound on the level-0 bound of k1_max.cuh,
+//            |X| <= sum_n |x_n w_n|, for ANY geometry (zero-filled input, N = 8192, table windows): a tile whose spectra
+//            all fall below the running global maximum skips its transform; survivors are transformed in full.
+template <int N, bool INVERSE, int WIN, bool TMA, int FAST = 0, bool PRUNE = false>
 __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_kernel(const __grid_constant__ K1Params p) {
+    static_assert(!PRUNE || (FAST == 0 && !INVERSE), "PRUNE is a variant of the generic forward statistics pass");
+    __shared__ float run_s[2];   // PRUNE: thread 0's sample of the running maximum, double buffered by iteration parity
     using C = FftCfg<N>;
     constexpr bool F = (FAST != 0);
     constexpr bool TW_PERSIST = (N <= 4096);
@@ -208,6 +213,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
         float2* my_slot = ring + (size_t(slot) * C::SPB + g) * SLOT;
         float2* my_B = IPB ? my_slot : Bbuf + size_t(g) * C::SIZE_B;
 
+        if (PRUNE && tid == 0) run_s[it & 1] = *reinterpret_cast<volatile float*>(p.run_max2);
         if (TMA) {
             mbar_wait(&bars[slot], (it / STAGES) & 1);
         } else {
@@ -226,6 +232,37 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
         float2 v[C::E];
         stage0_load<C, WIN>(t, my_slot, (F || valid) ? n_in : 0, pad_left, in_shift, p.scale, p.win, wcol, p.win_rows, v);
         if (need_load_barrier) __syncthreads();
+        if (PRUNE) {
+            // level-0 bound on the windowed, zero-filled samples this thread already holds
+            float l1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < C::E; ++i) l1 += sqrt_approx(fmaf(v[i].x, v[i].x, v[i].y * v[i].y));
+            constexpr int LANES0 = C::T < 32 ? C::T : 32;
+#pragma unroll
+            for (int off = LANES0 / 2; off > 0; off >>= 1) l1 += __shfl_xor_sync(0xffffffffu, l1, off);
+            if (C::T > 32) {
+                constexpr int WPG0 = C::T / 32;
+                float* rv = red + size_t(g) * 64;
+                if ((t & 31) == 0) rv[t >> 5] = l1;
+                __syncthreads();
+                l1 = rv[0];
+#pragma unroll
+                for (int w = 1; w < WPG0; ++w) l1 += rv[w];
+            }
+            const bool skip_mine = !valid || (l1 * l1 * 1.0001f < run_s[it & 1]);
+            // (the barrier also orders thread 0's write of run_s and every thread's reads of the landing slot)
+            if (__syncthreads_and(skip_mine)) {
+                if (t == 0 && valid) p.absmax[spec] = 0.f;
+                if (TMA && tid == 0) {
+                    const long long nt = tile + (long long)STAGES * gridDim.x;
+                    if (nt < ntiles) {
+                        fence_proxy_async_smem();
+                        issue(nt, slot);
+                    }
+                }
+                continue;
+            }
+        }
         stage0_store<C, INVERSE, TW_PERSIST>(t, my_slot, v, tw_persist, tw0_base);
         __syncthreads();
         // ---- stage 1: R1-point DFTs, exchange B ----------------------------------------------------------
@@ -303,6 +340,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
             if (!(F && !do_index) && t == 0 && valid) {
                 p.absmax[spec] = sqrtf(best);
                 if (do_index) p.argmax[spec] = besti;
+                if (PRUNE) atomicMax(reinterpret_cast<int*>(p.run_max2), __float_as_int(best));
             }
         }
         if (do_store && valid) {

@@ -8,10 +8,10 @@
 
 namespace xmr {
 
-template <int N, bool INVERSE, int WIN, bool TMA, int FAST = 0>
+template <int N, bool INVERSE, int WIN, bool TMA, int FAST = 0, bool PRUNE = false>
 static cudaError_t launch_one(const K1Params& p, int max_ctas, cudaStream_t st) {
     using C = FftCfg<N>;
-    auto kern = k1_kernel<N, INVERSE, WIN, TMA, FAST>;
+    auto kern = k1_kernel<N, INVERSE, WIN, TMA, FAST, PRUNE>;
     constexpr size_t smem = K1Smem<N>::TOTAL;
     static thread_local int cached_dev = -1;
     static thread_local int ctas_per_wave = 0;
@@ -85,7 +85,12 @@ cudaError_t XMR_CAT(k1_launch_, XMR_N)(const K1Params& p, bool inverse, int win,
             return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE>(p, max_ctas, st);
         if (st_ && ph && p.absmax == nullptr)
             return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE | K1_FAST_PHASE>(p, max_ctas, st);
-        if (!st_ && stats) {
+#if XMR_N >= 512 && XMR_N <= 4096
+        constexpr bool HAS_MAX_KERNEL = true;
+#else
+        constexpr bool HAS_MAX_KERNEL = false;
+#endif
+        if (!st_ && stats && (p.run_max2 == nullptr || HAS_MAX_KERNEL)) {
             cudaError_t e = cudaMemsetAsync(p.absmax, 0, sizeof(float) * size_t(p.batch), st);   // atomicMax accumulators
             if (e != cudaSuccess) return e;
 #if XMR_N >= 512 && XMR_N <= 4096
@@ -93,6 +98,14 @@ cudaError_t XMR_CAT(k1_launch_, XMR_N)(const K1Params& p, bool inverse, int win,
 #endif
             return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STATS>(p, max_ctas, st);
         }
+    }
+    if (p.run_max2 != nullptr && p.out == nullptr && p.absmax != nullptr && p.argmax == nullptr) {
+        // statistics-only pass of any other geometry with a running maximum: prune on the level-0 bound
+        if (win == 1)
+            return tma ? launch_one<XMR_N, false, 1, true, 0, true>(p, max_ctas, st)
+                       : launch_one<XMR_N, false, 1, false, 0, true>(p, max_ctas, st);
+        return tma ? launch_one<XMR_N, false, 2, true, 0, true>(p, max_ctas, st)
+                   : launch_one<XMR_N, false, 2, false, 0, true>(p, max_ctas, st);
     }
     if (win == 1)
         return tma ? launch_one<XMR_N, false, 1, true>(p, max_ctas, st) : launch_one<XMR_N, false, 1, false>(p, max_ctas, st);
