@@ -20,9 +20,28 @@ from . import device as D
 from .vocab import ATTRS, COORDS, DIMS
 
 
+_GEO_CACHE: dict = {}
+
+
 def chain_geometry(n_in, time_coord, target_points, position, lb):
-    """Host metadata of the chain: padded time axis, window (incl. 1/sqrt(N)), frequency axis, pad_left."""
-    t = np.asarray(time_coord, dtype=np.float64)
+    """Host metadata of the chain: padded time axis, window (incl. 1/sqrt(N)), frequency axis, pad_left.
+
+    Memoised on the exact time coordinate (a repeated call on the same axis reuses the float64 tables and the window
+    already uploaded to the device: for small batches these host steps cost more than the kernels)."""
+    t = np.ascontiguousarray(time_coord, dtype=np.float64)
+    key = (int(n_in), None if target_points is None else int(target_points), position, None if lb is None else float(lb),
+           t.tobytes())
+    hit = _GEO_CACHE.get(key)
+    if hit is not None:
+        return hit
+    geo = _chain_geometry(n_in, t, target_points, position, lb)
+    if len(_GEO_CACHE) >= 32:
+        _GEO_CACHE.pop(next(iter(_GEO_CACHE)))
+    _GEO_CACHE[key] = geo
+    return geo
+
+
+def _chain_geometry(n_in, t, target_points, position, lb):
     n_out, pad_left = n_in, 0
     t_pad = t
     if target_points is not None and target_points > n_in:
@@ -42,6 +61,9 @@ def chain_geometry(n_in, time_coord, target_points, position, lb):
         window = np.exp(-np.pi * lb * t_pad) / np.sqrt(n_out)           # fid.py:136 with the ortho norm folded in
     delta = (t_pad[1] - t_pad[0]) if n_out > 1 else 1.0
     freqs = np.roll(np.fft.fftfreq(n_out, d=delta), n_out // 2)         # fourier.py:95, 31-32
+    for arr in (t_pad, window, freqs):
+        if arr is not None:
+            arr.setflags(write=False)        # shared by every caller of the memoised geometry
     return dict(n_out=n_out, pad_left=pad_left, t_pad=t_pad, window=window, freqs=freqs)
 
 
