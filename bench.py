@@ -200,7 +200,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -245,7 +245,6 @@ def run_ours(args):
         import torch.distributed as dist_mod
 
         dist = dist_mod
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -466,13 +465,29 @@ def run_ours(args):
         "roofline": roofline, "breakdown_ms": breakdown, "per_voxel": per_voxel, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches["n"], "clocks": clocks,
         "result": {"p0": last[0], "p1": last[1], "pivot": last[2]} if args.mode == "single" else None,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    """Print the ONE JSON line on the real stdout."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
     args = parse()
+    # stdout carries the JSON line and nothing else: file descriptor 1 is pointed at stderr for the rest of the run, so
+    # that native libraries which print to stdout (the NCCL version banner) cannot get in front of it
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) == 0:
             run_reference_arm(args)
