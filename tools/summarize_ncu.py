@@ -31,7 +31,7 @@ def launches(src, dst):
                 seq.append((r[ki], float(r[vi].replace(",", ""))))
             except ValueError:
                 pass
-    mine = [(n, v) for n, v in seq if any(s in n for s in ("k1_kernel", "k2_kernel", "search_", "argmax", "rows_kernel",
+    mine = [(n, v) for n, v in seq if any(s in n for s in ("k1_kernel", "k1_max_kernel", "k2_kernel", "search_", "argmax", "rows_kernel",
                                                            "zero_fill_kernel", "phase_each"))]
     # the last full step = the launches after the last-but-one K1 store (12 launches per step in mode=single)
     with open(dst, "w") as f:
