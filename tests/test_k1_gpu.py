@@ -259,3 +259,31 @@ def test_pruned_statistics_any_geometry(dev, n_in, n_out, pad_left, table):
     same = np.repeat(fid[:1], 70, axis=0)
     _pruned_vs_plain(dev, same, window, n_out=n_out, pad_left=pad_left)
     _pruned_vs_plain(dev, np.zeros((5, n_in), dtype=np.complex128), window, n_out=n_out, pad_left=pad_left)
+
+
+@pytest.mark.parametrize("n_out,factor", [(512, 2), (1024, 2), (2048, 2), (4096, 2), (8192, 2), (1024, 4), (2048, 4),
+                                          (4096, 4), (8192, 4)])
+def test_zero_filled_fast_variants(dev, n_out, factor):
+    """Input zero-filled at the end to 2x / 4x its length (zero_fill's default geometry) takes compile-time specialised
+    store / store+phase kernels that never load the zero part: same results as the oracle."""
+    import torch
+    from xmris_b200 import device as D
+
+    n_in = n_out // factor
+    rng = np.random.default_rng(n_out + 3)
+    x = _rand(rng, (301, n_in))
+    t = np.arange(n_in) / 5000.0
+    lb = 5.0
+    ref, freqs = orc.chain_to_spectrum(x.astype(np.complex128), 1, t, n_out, "end", lb)
+    _, t_pad, _ = orc.zero_fill(np.zeros(n_in), 0, t, n_out, "end")
+    w = np.exp(-np.pi * lb * t_pad) / np.sqrt(n_out)
+    xd = torch.from_numpy(x).to(dev)
+    spec, _, _ = D.fid_to_spectrum(xd, n_out=n_out, window=w)
+    assert max(rel_l2(g, r) for g, r in zip(spec.cpu().numpy(), ref)) < TOL
+    p0, p1, pivot = 77.5, -1903.25, float(freqs[n_out // 5])
+    refp, _ = orc.phase(ref, 1, freqs, p0, p1, pivot)
+    rng_ = freqs.max() - freqs.min()
+    b = (p1 / 360.0) * (freqs[1] - freqs[0]) / rng_
+    a = p0 / 360.0 + (p1 / 360.0) * (freqs[0] - pivot) / rng_
+    specp, _, _ = D.fid_to_spectrum(xd, n_out=n_out, window=w, phase_turns=(a, b))
+    assert max(rel_l2(g, r) for g, r in zip(specp.cpu().numpy(), refp)) < TOL

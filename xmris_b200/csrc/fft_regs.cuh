@@ -85,20 +85,30 @@ XMR_HD constexpr int bitrev(int v, int bits) {
 
 // In-place radix-2 decimation-in-frequency DFT of R points held at v[off + i*stride], i = 0..R-1.
 // Output k is left at position bitrev(k): callers read v[off + bitrev(k)*stride]  (free: indices are immediates).
-template <int R, bool INVERSE, int STRIDE = 1>
+// NZ < R: only inputs 0 .. NZ-1 can be non-zero (input zero-filled at the end by a factor R/NZ): as long as a butterfly's
+// partner lies in the zero part the layer degenerates to a copy and a twiddle multiply (a + 0, (a - 0) * w), and within
+// every half-block again only the first NZ entries are non-zero.
+template <int R, bool INVERSE, int STRIDE = 1, int NZ = R>
 XMR_HD void dft_dif(float2* v, int off = 0) {
     static_assert(R >= 1 && R <= 32 && (R & (R - 1)) == 0, "radix must be a power of two <= 32");
+    static_assert(NZ >= 1 && NZ <= R && (NZ & (NZ - 1)) == 0, "NZ must be a power of two <= R");
     XMR_UNROLL
     for (int len = R; len >= 2; len >>= 1) {
         const int half = len >> 1;
         XMR_UNROLL
         for (int blk = 0; blk < R; blk += len) {
-            XMR_UNROLL
-            for (int j = 0; j < half; ++j) {
-                const int i0 = off + (blk + j) * STRIDE, i1 = off + (blk + j + half) * STRIDE;
-                const float2 a = v[i0], b = v[i1];
-                v[i0] = cadd(a, b);
-                v[i1] = mul_w32<INVERSE>(csub(a, b), j * (32 / len));
+            if (half >= NZ) {
+                XMR_UNROLL
+                for (int j = 0; j < NZ; ++j)
+                    v[off + (blk + j + half) * STRIDE] = mul_w32<INVERSE>(v[off + (blk + j) * STRIDE], j * (32 / len));
+            } else {
+                XMR_UNROLL
+                for (int j = 0; j < half; ++j) {
+                    const int i0 = off + (blk + j) * STRIDE, i1 = off + (blk + j + half) * STRIDE;
+                    const float2 a = v[i0], b = v[i1];
+                    v[i0] = cadd(a, b);
+                    v[i1] = mul_w32<INVERSE>(csub(a, b), j * (32 / len));
+                }
             }
         }
     }

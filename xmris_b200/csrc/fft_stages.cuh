@@ -84,12 +84,13 @@ XMR_HD void stage0_load(int t, const float2* slot, int n_in, int pad_left, int i
 // must put a block barrier between stage0_load and stage0_store.  Otherwise each thread reads and writes the same
 // set of addresses and exchange A happens in place without a barrier.
 // stage0_compute leaves Y[k1][n2] (inter-stage twiddle applied) at v[j*R0 + k1]; stage0_write stores it as exchange A.
-template <class C, bool INVERSE, bool TW_PERSIST>
+// ZF: the input is zero-filled at the end by this factor (1, 2, 4 ...; <= R0): rows n1 >= R0/ZF of every column are zero.
+template <class C, bool INVERSE, bool TW_PERSIST, int ZF = 1>
 XMR_HD void stage0_compute(int t, float2* v /* [E] */, const float2* tw_persist /* [C0][R0-1] */,
                            const float2* tw_base /* [C0][2] */) {
     XMR_UNROLL
     for (int j = 0; j < C::C0; ++j) {
-        dft_dif<C::R0, INVERSE>(v + j * C::R0);
+        dft_dif<C::R0, INVERSE, 1, (C::R0 / ZF >= 1 ? C::R0 / ZF : 1)>(v + j * C::R0);
         float2 w[C::R0 > 1 ? C::R0 : 2];
         if (!TW_PERSIST && C::R0 > 1) twiddle_powers<C::R0>(tw_base[2 * j], tw_base[2 * j + 1], w);
         float2 y[C::R0];
@@ -111,10 +112,10 @@ XMR_HD void stage0_write(int t, float2* slot, const float2* v /* [E] */) {
         for (int k1 = 0; k1 < C::R0; ++k1) slot[k1 * C::M + n2] = v[j * C::R0 + k1];
     }
 }
-template <class C, bool INVERSE, bool TW_PERSIST>
+template <class C, bool INVERSE, bool TW_PERSIST, int ZF = 1>
 XMR_HD void stage0_store(int t, float2* slot, float2* v /* [E] */, const float2* tw_persist /* [C0][R0-1] */,
                          const float2* tw_base /* [C0][2] */) {
-    stage0_compute<C, INVERSE, TW_PERSIST>(t, v, tw_persist, tw_base);
+    stage0_compute<C, INVERSE, TW_PERSIST, ZF>(t, v, tw_persist, tw_base);
     stage0_write<C>(t, slot, v);
 }
 

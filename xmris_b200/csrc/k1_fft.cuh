@@ -74,9 +74,11 @@ __device__ __forceinline__ void amax_combine(float& v, int& i, float ov, int oi)
 // WIN: 1 = full window table p.win[N]; 2 = separable p.win[column] * p.win_rows[row] (also "scale only").
 // FAST == 0: generic kernel; geometry (n_in, pad_left, shifts) and the epilogue options (statistics, phase, store) are
 //            uniform run-time values.
-// FAST != 0: specialised hot path for n_in == N, no padding, no input rotation, out_shift == N/2, with the epilogue
-//            fixed at compile time (bit mask of K1_FAST_*): no per-element predicates or index arithmetic.
-enum : int { K1_FAST_ON = 1, K1_FAST_STORE = 2, K1_FAST_STATS = 4, K1_FAST_PHASE = 8 };
+// FAST != 0: specialised hot path for n_in == N (or, with K1_FAST_ZF2 / ZF4, n_in == N/2 / N/4 zero-filled at the end: the
+//            zero rows of every stage-0 column are never loaded and the first butterfly layers degenerate), no left
+//            padding, no input rotation, out_shift == N/2, with the epilogue fixed at compile time (bit mask of
+//            K1_FAST_*): no per-element predicates or index arithmetic.
+enum : int { K1_FAST_ON = 1, K1_FAST_STORE = 2, K1_FAST_STATS = 4, K1_FAST_PHASE = 8, K1_FAST_ZF2 = 16, K1_FAST_ZF4 = 32 };
 
 // PRUNE (generic statistics-only launches with p.run_max2 set): branch and bound on the level-0 bound of k1_max.cuh,
 //            |X| <= sum_n |x_n w_n|, for ANY geometry (zero-filled input, N = 8192, table windows): a tile whose spectra
@@ -87,6 +89,8 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
     __shared__ float run_s[2];   // PRUNE: thread 0's sample of the running maximum, double buffered by iteration parity
     using C = FftCfg<N>;
     constexpr bool F = (FAST != 0);
+    constexpr int ZF = (FAST & K1_FAST_ZF4) ? 4 : ((FAST & K1_FAST_ZF2) ? 2 : 1);   // zero-fill factor of the fast variants
+    static_assert(FftCfg<N>::R0 >= ZF, "the zero-fill fast variants need a first radix >= the zero-fill factor");
     constexpr bool TW_PERSIST = (N <= 4096);
     constexpr int NTW = (C::R0 > 1) ? C::C0 * (C::R0 - 1) : 1;
     constexpr bool TW1_TAB_ = (K1Smem<N>::TW1 != 0);
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
     const int t = tid % C::T;     // thread within the spectrum
 
     const long long ntiles = (p.batch + C::SPB - 1) / C::SPB;
-    const int n_in = F ? C::N : p.n_in;
+    const int n_in = F ? C::N / ZF : p.n_in;
     const int pad_left = F ? 0 : p.pad_left;
     const int in_shift = F ? 0 : p.in_shift;
     const int out_shift = F ? C::N / 2 : p.out_shift;
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
                 continue;
             }
         }
-        stage0_store<C, INVERSE, TW_PERSIST>(t, my_slot, v, tw_persist, tw0_base);
+        stage0_store<C, INVERSE, TW_PERSIST, ZF>(t, my_slot, v, tw_persist, tw0_base);
         __syncthreads();
         // ---- stage 1: R1-point DFTs, exchange B ----------------------------------------------------------
         if (IPB) {

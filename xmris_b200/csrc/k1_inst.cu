@@ -99,6 +99,24 @@ cudaError_t XMR_CAT(k1_launch_, XMR_N)(const K1Params& p, bool inverse, int win,
             return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STATS>(p, max_ctas, st);
         }
     }
+#if XMR_N >= 512
+    // input zero-filled at the end to 2x / 4x its length (zero_fill's default geometry): store variants
+    if (tma && win == 2 && p.pad_left == 0 && p.in_shift == 0 && p.out_shift == XMR_N / 2 && p.out != nullptr &&
+        p.absmax == nullptr) {
+        if (2 * p.n_in == XMR_N) {
+            if (p.phase_on != 0)
+                return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE | K1_FAST_PHASE | K1_FAST_ZF2>(p, max_ctas, st);
+            return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE | K1_FAST_ZF2>(p, max_ctas, st);
+        }
+#if XMR_N >= 1024
+        if (4 * p.n_in == XMR_N) {
+            if (p.phase_on != 0)
+                return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE | K1_FAST_PHASE | K1_FAST_ZF4>(p, max_ctas, st);
+            return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE | K1_FAST_ZF4>(p, max_ctas, st);
+        }
+#endif
+    }
+#endif
     if (p.run_max2 != nullptr && p.out == nullptr && p.absmax != nullptr && p.argmax == nullptr) {
         // statistics-only pass of any other geometry with a running maximum: prune on the level-0 bound
         if (win == 1)
