@@ -240,7 +240,9 @@ def test_pruned_statistics_pick_the_exact_winner(dev, n):
     _pruned_vs_plain(dev, fid[:500], window * np.where((np.arange(n) // min(n, 256)) % 2 == 1, -1.0, 1.0))
 
 
-@pytest.mark.parametrize("n_in,n_out,pad_left,table", [(4096, 8192, 0, False), (8192, 8192, 0, False), (1024, 2048, 0, False),
+@pytest.mark.parametrize("n_in,n_out,pad_left,table", [(2048, 4096, 0, False), (1024, 4096, 0, False), (256, 512, 0, False),
+                                                       (256, 1024, 0, False), (512, 2048, 0, False), (128, 512, 0, False),
+                                                       (4096, 8192, 0, False), (8192, 8192, 0, False), (1024, 2048, 0, False),
                                                        (1024, 4096, 1536, False), (2048, 2048, 0, True), (100, 256, 0, False),
                                                        (64, 64, 0, False), (1000, 4096, 7, True)])
 def test_pruned_statistics_any_geometry(dev, n_in, n_out, pad_left, table):

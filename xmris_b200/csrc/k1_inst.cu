@@ -39,9 +39,10 @@ static cudaError_t launch_one(const K1Params& p, int max_ctas, cudaStream_t st) 
 }
 
 #if XMR_N >= 512 && XMR_N <= 4096
+template <int ZF = 1>
 static cudaError_t launch_max(const K1Params& p, cudaStream_t st) {
     using C = FftCfg<XMR_N>;
-    auto kern = k1_max_kernel<XMR_N>;
+    auto kern = k1_max_kernel<XMR_N, ZF>;
     constexpr size_t smem = K1MaxSmem<XMR_N>::TOTAL;
     static thread_local int cached_dev = -1;
     static thread_local int ctas_per_wave = 0;
@@ -99,6 +100,18 @@ cudaError_t XMR_CAT(k1_launch_, XMR_N)(const K1Params& p, bool inverse, int win,
             return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STATS>(p, max_ctas, st);
         }
     }
+#if XMR_N >= 512 && XMR_N <= 4096
+    // the same geometry, statistics only with a running maximum: the branch-and-bound kernel on the short rows
+    if (tma && win == 2 && p.pad_left == 0 && p.in_shift == 0 && p.out_shift == XMR_N / 2 && p.out == nullptr &&
+        p.absmax != nullptr && p.argmax == nullptr && p.run_max2 != nullptr && (2 * p.n_in == XMR_N || 4 * p.n_in == XMR_N)) {
+        cudaError_t e = cudaMemsetAsync(p.absmax, 0, sizeof(float) * size_t(p.batch), st);
+        if (e != cudaSuccess) return e;
+        if (2 * p.n_in == XMR_N) return launch_max<2>(p, st);
+#if XMR_N >= 1024
+        return launch_max<4>(p, st);
+#endif
+    }
+#endif
 #if XMR_N >= 512
     // input zero-filled at the end to 2x / 4x its length (zero_fill's default geometry): store variants
     if (tma && win == 2 && p.pad_left == 0 && p.in_shift == 0 && p.out_shift == XMR_N / 2 && p.out != nullptr &&

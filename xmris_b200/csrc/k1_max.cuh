@@ -1,5 +1,6 @@
 // K1-max: pass 1 of autophase(mode="single") -- per-spectrum max |S| for the global argmax (phasing.py:229-231), with
-// branch and bound.  Specialised for full-length input, separable window, fftshift-free statistics, N in [512, 4096].
+// branch and bound.  Specialised for full-length input or input zero-filled 2x / 4x at the end, separable window,
+// fftshift-free statistics, N in [512, 4096].
 //
 // Two upper bounds on every output of a spectrum, each far cheaper than finishing the transform:
 //   level 0 (no transform):                          |X| <= sum_n |x_n| |w_n|                      (triangle inequality)
@@ -31,11 +32,15 @@ struct K1MaxSmem {
     static constexpr size_t TOTAL = RING + RED + BAR + TW1;
 };
 
-template <int N>
+// ZF: the input holds N/ZF points and is zero-filled at the end (zero_fill's default geometry): only the first R0/ZF rows
+// of a stage-0 column are loaded, bounded and -- for survivors -- transformed (degenerate first butterfly layers).
+template <int N, int ZF = 1>
 __global__ void __launch_bounds__(FftCfg<N>::THREADS, 2) k1_max_kernel(const __grid_constant__ K1Params p) {
     using C = FftCfg<N>;
     using SM = K1MaxSmem<N>;
     static_assert(C::E == 16 && C::R1 == 16 && C::R2 == 16 && C::T >= 32, "k1_max_kernel: N in [512, 4096]");
+    static_assert(ZF >= 1 && C::R0 >= ZF && (ZF & (ZF - 1)) == 0, "zero-fill factor: a power of two <= R0");
+    constexpr int NR = C::R0 / ZF;       // non-zero rows of a stage-0 column
     constexpr int NTW = C::C0 * (C::R0 - 1);
     constexpr int WPG = C::T / 32;
 
@@ -60,10 +65,10 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, 2) k1_max_kernel(const __g
     auto issue = [&](long long tile, int slot) {
         const long long s0 = tile * C::SPB;
         const int nvalid = int((p.batch - s0) < C::SPB ? (p.batch - s0) : C::SPB);
-        constexpr uint32_t row_bytes = uint32_t(C::N) * 8u;
+        constexpr uint32_t row_bytes = uint32_t(C::N / ZF) * 8u;
         mbar_arrive_expect_tx(&bars[slot], row_bytes * nvalid);
         float2* dst = ring + size_t(slot) * C::SPB * SM::SLOT;
-        for (int r = 0; r < nvalid; ++r) bulk_g2s(dst + size_t(r) * SM::SLOT, p.in + (s0 + r) * C::N, row_bytes, &bars[slot]);
+        for (int r = 0; r < nvalid; ++r) bulk_g2s(dst + size_t(r) * SM::SLOT, p.in + (s0 + r) * (C::N / ZF), row_bytes, &bars[slot]);
     };
     if (tid == 0) {
         for (int s = 0; s < K1MAX_STAGES; ++s) mbar_init(&bars[s], 1);
@@ -98,9 +103,13 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, 2) k1_max_kernel(const __g
             float cj = 0.f;
 #pragma unroll
             for (int n1 = 0; n1 < C::R0; ++n1) {
-                const float2 x = valid ? my_slot[C::M * n1 + t + C::T * j] : make_float2(0.f, 0.f);
-                v[j * C::R0 + n1] = x;
-                cj = fmaf(sqrt_approx(fmaf(x.x, x.x, x.y * x.y)), fabsf(p.win_rows[n1]), cj);
+                if (n1 < NR) {
+                    const float2 x = valid ? my_slot[C::M * n1 + t + C::T * j] : make_float2(0.f, 0.f);
+                    v[j * C::R0 + n1] = x;
+                    cj = fmaf(sqrt_approx(fmaf(x.x, x.x, x.y * x.y)), fabsf(p.win_rows[n1]), cj);
+                } else {
+                    v[j * C::R0 + n1] = make_float2(0.f, 0.f);
+                }
             }
             l1 = fmaf(cj, fabsf(wcol[j]), l1);
         }
@@ -129,8 +138,8 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, 2) k1_max_kernel(const __g
 #pragma unroll
                 for (int j = 0; j < C::C0; ++j)
 #pragma unroll
-                    for (int n1 = 0; n1 < C::R0; ++n1) v[j * C::R0 + n1] = cscale(v[j * C::R0 + n1], wcol[j] * p.win_rows[n1]);
-                stage0_compute<C, false, true>(t, v, tw_persist, tw0_base);
+                    for (int n1 = 0; n1 < NR; ++n1) v[j * C::R0 + n1] = cscale(v[j * C::R0 + n1], wcol[j] * p.win_rows[n1]);
+                stage0_compute<C, false, true, ZF>(t, v, tw_persist, tw0_base);
                 stage0_write<C>(t, my_slot, v);
             }
             __syncthreads();
