@@ -391,7 +391,7 @@ def run_ours(args):
             sa, sb = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
             barrier()
             t1 = time.perf_counter()
-            for _ in range(2):
+            for _ in range(4):
                 if h2d:
                     with torch.cuda.stream(sa):
                         pipe.d_ins[0].copy_(h_in, non_blocking=True)
@@ -400,7 +400,7 @@ def run_ours(args):
                         h_out.copy_(pipe.d_ins[1], non_blocking=True)
             sa.synchronize()
             sb.synchronize()
-            return 2 * eb * n * 8 / (time.perf_counter() - t1) / 1e9
+            return 4 * eb * n * 8 / (time.perf_counter() - t1) / 1e9
 
         up, down, both = copy_rate(True, False), copy_rate(False, True), copy_rate(True, True)
         e2e["pcie"] = {"h2d_gbs": up, "d2h_gbs": down, "duplex_each_way_gbs": both,
