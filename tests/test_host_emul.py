@@ -73,3 +73,28 @@ def test_to_fid_inverse_with_input_unshift(emul, n):
     ref, _ = orc.to_fid(s.astype(np.complex128), 1, freqs)
     got = run(emul, s, n, inverse=1, in_shift=n // 2, out_shift=0)
     assert rel_l2(got, ref) < 5e-7
+
+
+@pytest.mark.parametrize("n_out,zf", [(512, 2), (1024, 2), (2048, 2), (4096, 2), (8192, 2), (1024, 4), (2048, 4), (4096, 4),
+                                      (8192, 4)])
+@pytest.mark.parametrize("persist", [0, 1])
+def test_zero_filled_fast_variant_choreography(emul, n_out, zf, persist):
+    """K1_FAST_ZF2 / ZF4: the zero rows of a stage-0 column are never read and the first butterfly layers degenerate."""
+    lib = ctypes.CDLL(os.path.join(CSRC, "libxmris_emul.so"))
+    f = lib.xmr_emul_fft_zf_c64
+    vp, i = ctypes.c_void_p, ctypes.c_int
+    f.argtypes = [vp, vp, ctypes.c_longlong, i, i, vp, ctypes.c_float, vp, i]
+    f.restype = i
+    n_in = n_out // zf
+    rng = np.random.default_rng(n_out + zf)
+    x = (rng.standard_normal((3, n_in)) + 1j * rng.standard_normal((3, n_in))).astype(np.complex64)
+    t = np.arange(n_in) * 2e-4
+    ref, _ = orc.chain_to_spectrum(x.astype(np.complex128), 1, t, n_out, "end", 5.0)
+    _, t_pad, _ = orc.zero_fill(np.zeros(n_in), 0, t, n_out, "end")
+    w = np.ascontiguousarray(np.exp(-np.pi * 5.0 * t_pad) / np.sqrt(n_out), dtype=np.float32)
+    # poison the part of the table that belongs to the zero rows: the fast variant must never touch it
+    w[n_in:] = np.nan
+    out = np.zeros((3, n_out), np.complex64)
+    tw = np.exp(-2j * np.pi * np.arange(n_out) / n_out).astype(np.complex64)
+    assert f(x.ctypes.data, out.ctypes.data, 3, n_out, zf, w.ctypes.data, 1.0 / np.sqrt(n_out), tw.ctypes.data, persist) == 0
+    assert rel_l2(out, ref) < 5e-7

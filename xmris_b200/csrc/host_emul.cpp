@@ -13,7 +13,7 @@
 
 using namespace xmr;
 
-template <int N, bool INVERSE>
+template <int N, bool INVERSE, int ZF = 1>
 static void emul_one(const float2* in, float2* out, int n_in, int pad_left, int in_shift, const float* wtab, float scale,
                      const float2* twN, int shift, bool tw_persist_mode) {
     using C = FftCfg<N>;
@@ -34,10 +34,10 @@ static void emul_one(const float2* in, float2* out, int n_in, int pad_left, int 
     }
     for (int t = 0; t < C::T; ++t) {
         if (tw_persist_mode)
-            stage0_store<C, INVERSE, true>(t, slot.data(), &regs[size_t(t) * C::E],
+            stage0_store<C, INVERSE, true, ZF>(t, slot.data(), &regs[size_t(t) * C::E],
                                            &twp[size_t(t) * C::C0 * (C::R0 > 1 ? C::R0 - 1 : 1)], &tw0[size_t(t) * C::C0 * 2]);
         else
-            stage0_store<C, INVERSE, false>(t, slot.data(), &regs[size_t(t) * C::E],
+            stage0_store<C, INVERSE, false, ZF>(t, slot.data(), &regs[size_t(t) * C::E],
                                             &twp[size_t(t) * C::C0 * (C::R0 > 1 ? C::R0 - 1 : 1)], &tw0[size_t(t) * C::C0 * 2]);
     }
     // __syncthreads
@@ -74,6 +74,30 @@ extern "C" int xmr_emul_fft_c64(const float* in, float* out, long long batch, in
             default: return 2;
         }
 #undef XMR_CASE
+    }
+    return 0;
+}
+
+// The zero-fill fast variants (K1_FAST_ZF2 / ZF4): input of n_out/zf points zero-filled at the end; the degenerate first
+// butterfly layers of dft_dif<R0, ..., NZ = R0/zf> run in place of the full ones.
+extern "C" int xmr_emul_fft_zf_c64(const float* in, float* out, long long batch, int n_out, int zf, const float* wtab,
+                                   float scale, const float* twN, int tw_persist) {
+    const float2* fin = reinterpret_cast<const float2*>(in);
+    float2* fout = reinterpret_cast<float2*>(out);
+    const float2* tw = reinterpret_cast<const float2*>(twN);
+    const int n_in = n_out / zf;
+    for (long long b = 0; b < batch; ++b) {
+        const float2* src = fin + b * n_in;
+        float2* dst = fout + b * n_out;
+#define XMR_CASE(NN, ZZ)                                                                                     \
+    if (n_out == NN && zf == ZZ) {                                                                           \
+        emul_one<NN, false, ZZ>(src, dst, n_in, 0, 0, wtab, scale, tw, NN / 2, tw_persist != 0);             \
+        continue;                                                                                            \
+    }
+        XMR_CASE(512, 2) XMR_CASE(1024, 2) XMR_CASE(2048, 2) XMR_CASE(4096, 2) XMR_CASE(8192, 2)
+        XMR_CASE(1024, 4) XMR_CASE(2048, 4) XMR_CASE(4096, 4) XMR_CASE(8192, 4)
+#undef XMR_CASE
+        return 2;
     }
     return 0;
 }
