@@ -5,7 +5,8 @@ import torch
 from xmris_b200 import chain
 from xmris_b200.synth import make_fids_torch
 dev = torch.device("cuda:0")
-for n_in, zf, batch in [(4096, None, 262144), (2048, 4096, 262144), (1024, 4096, 262144), (2048, None, 524288), (1024, 2048, 524288),
+CASES = [tuple(int(v) if v != "None" else None for v in a.split(",")) for a in sys.argv[1:]]   # "n_in,n_out|None,batch"
+for n_in, zf, batch in CASES or [(4096, None, 262144), (2048, 4096, 262144), (1024, 4096, 262144), (2048, None, 524288), (1024, 2048, 524288),
                         (4096, 8192, 131072), (8192, None, 131072), (2048, 8192, 131072), (1024, None, 1 << 20), (512, 1024, 1 << 20)]:
     fid, t = make_fids_torch("1H", batch, n_in, dev, seed=1)
     n_out = zf or n_in
