@@ -52,9 +52,14 @@ def make_exchange(dist, device, n_out: int, row_offset_elems: int):
     def exchange(local_max, local_flat, search_fn):
         mine = torch.tensor([float(local_max), float(rank), float(local_flat), float(row_offset_elems)],
                             dtype=torch.float64, device=device)
-        gathered = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(gathered, mine)
-        table = torch.stack(gathered).cpu().numpy()
+        flat = torch.empty(world * 4, dtype=torch.float64, device=device)
+        try:
+            dist.all_gather_into_tensor(flat, mine)            # one collective (NCCL; recent gloo)
+        except (RuntimeError, NotImplementedError, AttributeError):
+            gathered = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(gathered, mine)
+            flat = torch.cat(gathered)
+        table = flat.cpu().numpy().reshape(world, 4)
         winner, _ = pick_winner(table[:, 0], table[:, 2], table[:, 3])
         res = torch.zeros(4, dtype=torch.float64, device=device)
         if rank == winner:
