@@ -39,11 +39,24 @@ static cudaError_t launch_one(const K1Params& p, int max_ctas, cudaStream_t st) 
 }
 
 #if XMR_N >= 512 && XMR_N <= 4096
+template <int ZF>
+struct K1MaxPick {
+    static constexpr auto kern = k1_max_zf_kernel<XMR_N, ZF>;
+    static constexpr size_t smem = K1MaxZfSmem<XMR_N, ZF>::TOTAL;
+    static constexpr long long spt = (long long)ZF * FftCfg<XMR_N>::SPB;     // spectra per loop iteration
+};
+template <>
+struct K1MaxPick<1> {
+    static constexpr auto kern = k1_max_kernel<XMR_N, 1>;
+    static constexpr size_t smem = K1MaxSmem<XMR_N>::TOTAL;
+    static constexpr long long spt = FftCfg<XMR_N>::SPB;
+};
+
 template <int ZF = 1>
 static cudaError_t launch_max(const K1Params& p, cudaStream_t st) {
     using C = FftCfg<XMR_N>;
-    auto kern = k1_max_kernel<XMR_N, ZF>;
-    constexpr size_t smem = K1MaxSmem<XMR_N>::TOTAL;
+    auto kern = K1MaxPick<ZF>::kern;
+    constexpr size_t smem = K1MaxPick<ZF>::smem;
     static thread_local int cached_dev = -1;
     static thread_local int ctas_per_wave = 0;
     int dev = 0;
@@ -60,7 +73,7 @@ static cudaError_t launch_max(const K1Params& p, cudaStream_t st) {
         ctas_per_wave = (per_sm < 1 ? 1 : per_sm) * sms;
         cached_dev = dev;
     }
-    const long long ntiles = (p.batch + C::SPB - 1) / C::SPB;
+    const long long ntiles = (p.batch + K1MaxPick<ZF>::spt - 1) / K1MaxPick<ZF>::spt;
     const long long grid = ntiles < ctas_per_wave ? ntiles : ctas_per_wave;
     if (grid < 1) return cudaSuccess;
     kern<<<dim3((unsigned)grid), dim3(C::THREADS), smem, st>>>(p);
