@@ -169,6 +169,20 @@ int xmr_chain_host_c64(const xmr_host_chain_desc* desc, const void* fid_host, vo
                        double* result_host, double* p0_host, double* p1_host, int* pivot_host, float* fun_host);
 int xmr_host_workspace_release(void);
 
+/* The mode="single" chain on DEVICE-resident data in one call (the reference's `.xmr.zero_fill().xmr.apodize_exp()
+ * .xmr.to_spectrum().xmr.autophase()` on an array that already lives in HBM): branch-and-bound pass 1 -> global argmax
+ * (phasing.py:229-231) -> the winning spectrum -> (p0, p1) search (phasing.py:270-287) -> pass 2 with the fused phase
+ * (phasing.py:289-290).  Only `n_in, n_out, pad_left, scale, method, index_width, p0_only, fixed_pivot, u0_fixed,
+ * fixed_target, du` of the descriptor are read; the window is passed as prepared for xmr_fid_to_spectrum_c64
+ * (window_mode / window_dev / win_rows_host).
+ *   workspace_dev  at least xmr_chain_single_workspace_bytes(batch, n_out) bytes of device memory, caller-owned
+ *   result_host    double[6] = {p0 deg, p1 deg, pivot index on the output axis, objective, global max |S|, winning row}
+ * Synchronises `stream` three times (16 + 4 + 32 bytes read back); pass 2 is enqueued when it returns. */
+int64_t xmr_chain_single_workspace_bytes(int64_t batch, int n_out);
+int xmr_chain_single_dev_c64(const xmr_host_chain_desc* desc, const void* fid_dev, void* spec_dev, int64_t batch,
+                             int window_mode, const float* window_dev, const float* win_rows_host, void* workspace_dev,
+                             double* result_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -147,6 +147,8 @@ def chain_single(fid_t, time_coord, target_points=None, position="end", lb=None,
     n_in = fid_t.shape[-1]
     flat = fid_t.reshape(-1, n_in)
     geo = chain_geometry(n_in, time_coord, target_points, position, lb)
+    if exchange is None and autophase_lb == 0 and geo["n_out"] in D.SUPPORTED_N and flat.shape[0] > 0:
+        return _chain_single_one_call(fid_t, flat, geo, method, peak_width, target_coord, p0_only, out)
     vmax, findex = local_stats(flat, geo)
 
     def search():
@@ -157,6 +159,25 @@ def chain_single(fid_t, time_coord, target_points=None, position="end", lb=None,
     spec = apply_pass(flat, geo, p0, p1, pivot, out=out)
     spec = spec.reshape(tuple(fid_t.shape[:-1]) + (geo["n_out"],))
     return spec, geo["freqs"], dict(p0=p0, p1=p1, pivot=pivot, fun=fun, n_out=geo["n_out"], pad_left=geo["pad_left"])
+
+
+def _chain_single_one_call(fid_t, flat, geo, method, peak_width, target_coord, p0_only, out):
+    """Single-GPU ``mode="single"`` chain through ``xmr_chain_single_dev_c64`` (one C call, three small read-backs)."""
+    from .processing import _index_width
+
+    n_out, freqs = geo["n_out"], geo["freqs"]
+    x_range = float(freqs.max()) - float(freqs.min())
+    du = (freqs[-1] - freqs[0]) / (n_out - 1) / x_range
+    fixed = None
+    if target_coord is not None:
+        fixed = ((freqs[0] - float(target_coord)) / x_range, int(np.argmin(np.abs(freqs - target_coord))))
+    spec, res = D.chain_single_dev(flat, n_out, geo["pad_left"], _win(geo, flat.device), du, method,
+                                   _index_width(freqs, peak_width), p0_only, fixed,
+                                   out=None if out is None else out.reshape(-1, n_out))
+    pivot = float(target_coord) if target_coord is not None else float(freqs[int(res[2])])
+    spec = spec.reshape(tuple(fid_t.shape[:-1]) + (n_out,))
+    return spec, freqs, dict(p0=res[0], p1=0.0 if p0_only else res[1], pivot=pivot, fun=res[3], n_out=n_out,
+                             pad_left=geo["pad_left"])
 
 
 def chain_to_spectrum(fid_t, time_coord, target_points=None, position="end", lb=None, out=None):

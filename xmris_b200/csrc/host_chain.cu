@@ -323,4 +323,86 @@ int xmr_chain_host_c64(const xmr_host_chain_desc* d, const void* fid_host, void*
 #undef XMR_CUC
 }
 
+// ---- the same chain on DEVICE-resident data: autophase(mode="single") end to end in one call ---------------------------
+// (what the survey's proposed `xmr_autophase_c64(fid, out, ..., mode=single)` asks for: pass 1 with branch and bound ->
+// global argmax -> the winning spectrum -> (p0, p1) search -> pass 2 with the fused phase; three small device->host reads,
+// no host code between the launches but the winner bookkeeping.)
+int64_t xmr_chain_single_workspace_bytes(int64_t batch, int n_out) {
+    if (batch < 0 || n_out < 1) return 0;
+    return int64_t(align_up(size_t(batch) * 4, 256) + 256 + align_up(size_t(n_out) * 8 + 64, 256) +
+                   size_t(xmr_autophase_workspace_bytes()));
+}
+
+int xmr_chain_single_dev_c64(const xmr_host_chain_desc* d, const void* fid_dev, void* spec_dev, int64_t batch, int window_mode,
+                             const float* window_dev, const float* win_rows_host, void* workspace_dev, double* result_host,
+                             void* stream) {
+    if (!d) return xmr_abi::fail(XMR_ERR_BAD_ARG, "descriptor is NULL");
+    const int n_in = d->n_in, n_out = d->n_out;
+    if (batch < 0 || n_in < 1 || n_out < n_in || d->pad_left < 0 || d->pad_left + n_in > n_out)
+        return xmr_abi::fail(XMR_ERR_BAD_ARG, "bad sizes: batch=%lld n_in=%d n_out=%d pad_left=%d", (long long)batch, n_in, n_out, d->pad_left);
+    if (!(n_out >= 16 && n_out <= 8192 && (n_out & (n_out - 1)) == 0))
+        return xmr_abi::fail(XMR_ERR_UNSUPPORTED_N, "n_out=%d: the device chain needs a power-of-two length in [16, 8192]", n_out);
+    if (batch == 0) return XMR_OK;
+    if (!fid_dev || !spec_dev || !workspace_dev || !result_host) return xmr_abi::fail(XMR_ERR_BAD_ARG, "NULL pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned char* sm = static_cast<unsigned char*>(workspace_dev);
+    const size_t o_arg = align_up(size_t(batch) * 4, 256);       // 16 B argmax record | running max at +32 | search result at +64
+    const size_t o_row = o_arg + 256;                             // one spectrum + its stats
+    const size_t o_sws = o_row + align_up(size_t(n_out) * 8 + 64, 256);
+    float* absmax = reinterpret_cast<float*>(sm);
+    const float scale = d->scale != 0.f ? d->scale : 1.0f / std::sqrt(float(n_out));
+    float ones[32];
+    for (float& r : ones) r = 1.0f;
+    const float* rows = win_rows_host ? win_rows_host : ones;
+    const size_t row_in = size_t(n_in) * 8, row_out = size_t(n_out) * 8;
+    int rc;
+#define XMR_RC(call)                  \
+    do {                              \
+        rc = (call);                  \
+        if (rc != XMR_OK) return rc;  \
+    } while (0)
+    XMR_RC(xmr_fid_absmax_pruned_c64(fid_dev, batch, n_in, n_out, d->pad_left, window_mode, window_dev, rows, scale, absmax,
+                                     reinterpret_cast<float*>(sm + o_arg + 32), 1, st));
+    XMR_RC(xmr_global_argmax(absmax, nullptr, batch, n_out, sm + o_arg, st));
+    unsigned char arg_h[16];
+    XMR_CU(cudaMemcpyAsync(arg_h, sm + o_arg, 16, cudaMemcpyDeviceToHost, st));
+    XMR_CU(cudaStreamSynchronize(st));
+    float vmax;
+    long long flat;
+    std::memcpy(&vmax, arg_h, 4);
+    std::memcpy(&flat, arg_h + 8, 8);
+    const long long row = flat / n_out;
+    unsigned char* rowbuf = sm + o_row;
+    float* row_abs = reinterpret_cast<float*>(rowbuf + row_out);
+    int* row_arg = reinterpret_cast<int*>(rowbuf + row_out + 16);
+    XMR_RC(xmr_fid_to_spectrum_c64(static_cast<const unsigned char*>(fid_dev) + size_t(row) * row_in, rowbuf, 1, n_in, n_out, d->pad_left,
+                                   window_mode, window_dev, rows, scale, 0, 0, n_out / 2, row_abs, row_arg, XMR_PHASE_NONE, 0.0, 0.0, st));
+    int idx = 0;
+    if (!d->fixed_pivot) {
+        XMR_CU(cudaMemcpyAsync(&idx, row_arg, 4, cudaMemcpyDeviceToHost, st));
+        XMR_CU(cudaStreamSynchronize(st));
+    }
+    const int target = d->fixed_pivot ? d->fixed_target : idx;
+    const double u0 = d->fixed_pivot ? d->u0_fixed : -d->du * double(idx);
+    double* res = reinterpret_cast<double*>(sm + o_arg + 64);
+    XMR_RC(xmr_autophase_search_c64(rowbuf, n_out, u0, d->du, d->method, target, d->index_width > 0 ? d->index_width : 1, d->p0_only, res,
+                                    sm + o_sws, st));
+    double res_h[4];
+    XMR_CU(cudaMemcpyAsync(res_h, res, 32, cudaMemcpyDeviceToHost, st));
+    XMR_CU(cudaStreamSynchronize(st));
+    const double p0 = res_h[0], p1 = d->p0_only ? 0.0 : res_h[1];
+    result_host[0] = p0;
+    result_host[1] = p1;
+    result_host[2] = double(target);
+    result_host[3] = res_h[2];
+    result_host[4] = double(vmax);
+    result_host[5] = double(row);
+    const double ph_a = p0 / 360.0 + (p1 / 360.0) * u0, ph_b = (p1 / 360.0) * d->du;
+    XMR_RC(xmr_fid_to_spectrum_c64(fid_dev, spec_dev, batch, n_in, n_out, d->pad_left, window_mode, window_dev, rows, scale, 0, 0, n_out / 2,
+                                   nullptr, nullptr, XMR_PHASE_UNIFORM, ph_a, ph_b, st));
+#undef XMR_RC
+    return XMR_OK;
+}
+
+
 }  // extern "C"

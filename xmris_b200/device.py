@@ -393,6 +393,61 @@ def _workspace(device):
     return ws
 
 
+_chain_workspaces: dict = {}
+
+
+def chain_single_dev(fid, n_out, pad_left, window, du, method="acme", index_width=1, p0_only=False, fixed=None, out=None,
+                     stream=None):
+    """``mode="single"`` chain on a device-resident ``[batch, n_in]`` tensor through ONE C-ABI call
+    (``xmr_chain_single_dev_c64``: pass 1, argmax, winning spectrum, search, pass 2 -- no Python between the launches).
+
+    ``window``: a :class:`PreparedWindow` or None; ``fixed``: ``None`` or ``(u0, target_idx)`` when ``target_coord`` is
+    given.  Returns ``(spectrum, result)`` with ``result = [p0, p1, pivot index, fun, max |S|, winning row]`` (host)."""
+    torch = _torch()
+    lib = _lib.load()
+    _require_cuda(fid, "fid")
+    if method not in _lib.METHODS:
+        raise ValueError("Method must be 'acme', 'peak_minima', or 'positivity'")
+    n_in = fid.shape[-1]
+    batch = fid.numel() // n_in
+    dev = fid.device
+    if out is None:
+        out = torch.empty((batch, n_out), dtype=torch.complex64, device=dev)
+    desc = _lib.HostChainDesc()
+    desc.n_in, desc.n_out, desc.pad_left = int(n_in), int(n_out), int(pad_left)
+    desc.scale = 0.0
+    desc.autophase_mode = 1
+    desc.method = _lib.METHODS[method]
+    desc.index_width = int(index_width)
+    desc.p0_only = int(bool(p0_only))
+    desc.du = float(du)
+    if fixed is not None:
+        desc.fixed_pivot = 1
+        desc.u0_fixed = float(fixed[0])
+        desc.fixed_target = int(fixed[1])
+    win_mode, win_dev, rows = _lib.WIN_NONE, None, None
+    if window is not None:
+        if not isinstance(window, PreparedWindow):
+            window = PreparedWindow(window, n_out, dev)
+        win_mode, win_dev, rows = window.mode, window.dev, window.rows
+    rows_arr = (ctypes.c_float * 32)(*([1.0] * 32))
+    if rows is not None:
+        for i, r in enumerate(rows):
+            rows_arr[i] = float(r)
+    need = int(lib.xmr_chain_single_workspace_bytes(batch, int(n_out)))
+    key = (dev.type, dev.index)
+    ws = _chain_workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        _chain_workspaces[key] = ws
+    result = (ctypes.c_double * 6)()
+    with torch.cuda.device(dev):
+        _lib.check(lib.xmr_chain_single_dev_c64(ctypes.byref(desc), _ptr(fid), _ptr(out), batch, win_mode, _ptr(win_dev),
+                                                ctypes.cast(rows_arr, ctypes.c_void_p), _ptr(ws),
+                                                ctypes.cast(result, ctypes.c_void_p), _stream_ptr(stream)))
+    return out, [float(v) for v in result]
+
+
 def autophase_search(spec1d, u0, du, method="acme", target_idx=0, index_width=1, p0_only=False, stream=None):
     """Global (p0, p1) search on one device-resident spectrum.  Returns a CUDA float64 tensor ``[p0, p1, fun, 0]``.
 
