@@ -60,9 +60,9 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
     cudaError_t e;
     e = cudaFuncSetAttribute(search_coarse_kernel<METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_coarse));
     if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "cudaFuncSetAttribute(search_coarse)");
-    e = cudaFuncSetAttribute(search_zoom_kernel<METHOD, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_zoom));
+    e = cudaFuncSetAttribute(search_zoom_kernel<METHOD, double, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_zoom));
     if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "cudaFuncSetAttribute(search_zoom)");
-    e = cudaFuncSetAttribute(search_zoom_kernel<METHOD, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_zoom));
+    e = cudaFuncSetAttribute(search_zoom_kernel<METHOD, float, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_zoom));
     if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "cudaFuncSetAttribute(search_zoom f32)");
 
     Cand* listA = ws;
@@ -114,7 +114,6 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
     zp.sep0 = 2.0 * sp.p0_step;
     zp.sep1 = p0_only ? 0.0 : 2.0 * sp.p1_step;
     const int levels = g_tuning.levels;
-    const int per_start = zp.rows * ZOOM_CHUNKS;
     int starts_prev = 0;
     double ratio_prev = 1.0;
     for (int lvl = 0; lvl < levels; ++lvl) {
@@ -139,11 +138,11 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
             zp.first_level = 0;
             zp.n_prev = n_prev;
         }
-        if (f32) search_zoom_kernel<METHOD, float><<<per_start * n_starts, SEARCH_THREADS, smem_zoom, st>>>(zp);
-        else search_zoom_kernel<METHOD, double><<<per_start * n_starts, SEARCH_THREADS, smem_zoom, st>>>(zp);
+        if (f32) search_zoom_kernel<METHOD, float, 8><<<zp.rows * (ZOOM_SPAN / 8) * n_starts, SEARCH_THREADS, smem_zoom, st>>>(zp);
+        else search_zoom_kernel<METHOD, double, 4><<<zp.rows * (ZOOM_SPAN / 4) * n_starts, SEARCH_THREADS, smem_zoom, st>>>(zp);
         e = cudaGetLastError();
         if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_zoom launch");
-        n_prev = per_start * SEARCH_K;                 // candidates per start
+        n_prev = zp.rows * ZOOM_SPAN;                  // candidates per start
         starts_prev = n_starts;
         prev = cur;
         cur = (cur == listB) ? listA : listB;
@@ -177,7 +176,7 @@ int xmr_row_absmax_c64(const void* spec_dev, int64_t batch, int n, float* absmax
 int xmr_autophase_search_tuning(double p0_step_deg, double p1_step_deg, int starts, int levels, int f32_levels,
                                 int late_starts, double first_ratio) {
     if (!(p0_step_deg > 0.0) || !(p1_step_deg > 0.0) || p0_step_deg > 45.0 || p1_step_deg > 500.0 || starts < 1 ||
-        starts > ZOOM_MAX_STARTS || levels < 1 || levels > 12 || starts * ZOOM_SIDE * ZOOM_CHUNKS * SEARCH_K > WS_LIST ||
+        starts > ZOOM_MAX_STARTS || levels < 1 || levels > 12 || starts * ZOOM_SIDE * ZOOM_SPAN > WS_LIST ||
         f32_levels < 0 || late_starts < 1 || !(first_ratio >= 1.0) || first_ratio > 10.0)
         return xmr_abi::fail(XMR_ERR_BAD_ARG, "search tuning: p0_step=%g p1_step=%g starts=%d levels=%d f32_levels=%d "
                              "late_starts=%d", p0_step_deg, p1_step_deg, starts, levels, f32_levels, late_starts);

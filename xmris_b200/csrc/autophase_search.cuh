@@ -98,7 +98,7 @@ struct ZoomParams {
     double h0, h1;      // half-widths of this level's window around the best previous candidate
     double p0_lo, p0_hi, p1_lo, p1_hi;
     int rows;           // 21 (two parameters) or 1 (p0 only)
-    Cand* cur;          // n_starts * rows * 3 * SEARCH_K candidates (one contiguous block per start)
+    Cand* cur;          // n_starts * rows * ZOOM_SPAN candidates (one contiguous block per start)
     int n_starts;       // basins refined in parallel (<= ZOOM_MAX_STARTS)
     int first_level;    // 1: prev is ONE list of n_prev candidates shared by all starts (start s takes the s-th best
                         //    DISTINCT one): the coarse grid's list, or all blocks of a level that ran more starts;
@@ -108,7 +108,7 @@ struct ZoomParams {
 
 constexpr int ZOOM_MAX_STARTS = 8;  // the best distinct coarse cells are refined side by side (63 CTAs each)
 constexpr int ZOOM_SIDE = 21;   // 21 x 21 points per level, spacing h/10
-constexpr int ZOOM_CHUNKS = 3;  // 3 * SEARCH_K = 24 >= 21
+constexpr int ZOOM_SPAN = 24;   // p0 slots per row (>= ZOOM_SIDE), split into chunks of K candidates
 
 __device__ __forceinline__ bool cand_distinct(const Cand& a, const Cand& b, double sep0, double sep1) {
     double d0 = fabs(a.p0 - b.p0);
@@ -159,18 +159,20 @@ __device__ __forceinline__ Cand block_argmin(const Cand* list, int n_list, const
 // ---- zoom level: one CTA per (p1 row, chunk of K p0 values), the 8 warps split the spectrum -----------------------
 // R = float for the wide early levels (spacing >= 0.1 deg: objective differences between neighbouring candidates are far
 // above float32 summation noise), double for the final ones.  Per-warp partial sums are combined and scored in double.
-template <int METHOD, typename R>
+// K: zero-order candidates per CTA (24/K chunks per p1 row): 8 for the float32 levels, 4 for the float64 ones, whose long
+// dependent chains per candidate profit more from twice the CTAs than from sharing the first-order rotation.
+template <int METHOD, typename R, int K>
 __global__ void __launch_bounds__(SEARCH_THREADS) search_zoom_kernel(const __grid_constant__ ZoomParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sp = reinterpret_cast<float2*>(smem_raw);
-    __shared__ double part[SEARCH_THREADS / 32][SEARCH_K][4];
+    __shared__ double part[SEARCH_THREADS / 32][K][4];
     const int n = p.n;
     constexpr int NW = SEARCH_THREADS / 32;
     const int per_warp = (n + NW - 1) / NW;
     const int L = (per_warp + 31) / 32;
     const int padshift = ilog2_ceil(L);
     load_padded(sp, p.spec, n, padshift);
-    const int per_start = p.rows * ZOOM_CHUNKS;
+    const int per_start = p.rows * (ZOOM_SPAN / K);
     const int start = blockIdx.x / per_start, local = blockIdx.x % per_start;
     Cand centre;                                          // (block_argmin contains the barriers that also publish `sp`)
     if (p.first_level) {
@@ -185,15 +187,15 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_zoom_kernel(const __gri
     }
     const bool dead = !(centre.f < CUDART_INF);           // no second basin: this start reports +inf
 
-    const int row = local / ZOOM_CHUNKS, ch = local % ZOOM_CHUNKS;
+    const int row = local / (ZOOM_SPAN / K), ch = local % (ZOOM_SPAN / K);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double p1 = (p.rows == 1) ? centre.p1
                                     : fmin(fmax(centre.p1 + (row - ZOOM_SIDE / 2) * (p.h1 / (ZOOM_SIDE / 2)), p.p1_lo), p.p1_hi);
-    R c0[SEARCH_K], s0[SEARCH_K];
-    double p0k[SEARCH_K];
+    R c0[K], s0[K];
+    double p0k[K];
 #pragma unroll
-    for (int k = 0; k < SEARCH_K; ++k) {
-        const int i = min(ch * SEARCH_K + k, ZOOM_SIDE - 1);
+    for (int k = 0; k < K; ++k) {
+        const int i = min(ch * K + k, ZOOM_SIDE - 1);
         // p0 is periodic: a window that leaves the closed box [-180, 180] re-enters on the other side
         double q0 = centre.p0 + (i - ZOOM_SIDE / 2) * (p.h0 / (ZOOM_SIDE / 2));
         q0 = q0 > p.p0_hi ? q0 - 360.0 : (q0 < p.p0_lo ? q0 + 360.0 : q0);
@@ -202,18 +204,18 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_zoom_kernel(const __gri
     }
     const int w0 = min(warp * per_warp, n), w1 = min(w0 + per_warp, n);
     const int m0 = min(w0 + (lane << padshift), w1), m1 = min(m0 + (1 << padshift), w1);
-    Acc<R, METHOD, SEARCH_K> acc;
+    Acc<R, METHOD, K> acc;
     acc.init();
-    lane_accumulate_rt<R, METHOD, SEARCH_K>(sp, padshift, m0, m1, p.geom, R(p1 / 360.0), R(p.u0), R(p.du), c0, s0, acc);
+    lane_accumulate_rt<R, METHOD, K>(sp, padshift, m0, m1, p.geom, R(p1 / 360.0), R(p.u0), R(p.du), c0, s0, acc);
     acc.warp_reduce();
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < SEARCH_K; ++k)
+        for (int k = 0; k < K; ++k)
 #pragma unroll
             for (int s = 0; s < 4; ++s) part[warp][k][s] = double(acc.a[k][s]);
     }
     __syncthreads();
-    if (threadIdx.x < SEARCH_K) {
+    if (threadIdx.x < K) {
         const int k = threadIdx.x;
         Acc<double, METHOD, 1> tot;
 #pragma unroll
@@ -228,12 +230,12 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_zoom_kernel(const __gri
         // select p0k[k] without dynamic register indexing
         double myp0 = p0k[0];
 #pragma unroll
-        for (int kk = 1; kk < SEARCH_K; ++kk)
+        for (int kk = 1; kk < K; ++kk)
             if (kk == k) myp0 = p0k[kk];
         c.p0 = myp0;
         c.p1 = p1;
         c.pad = 0;
-        p.cur[blockIdx.x * SEARCH_K + k] = c;
+        p.cur[blockIdx.x * K + k] = c;
     }
 }
 
