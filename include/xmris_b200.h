@@ -183,6 +183,18 @@ int xmr_chain_single_dev_c64(const xmr_host_chain_desc* desc, const void* fid_de
                              int window_mode, const float* window_dev, const float* win_rows_host, void* workspace_dev,
                              double* result_host, void* stream);
 
+/* baseline_als(da, dim, lam, p, n_iter) -- asymmetric least squares baseline correction of the REAL part, the step after
+ * autophase in the reference's pipeline (src/xmris/processing/baseline.py:10-119; accessor core/accessor.py:552-597).
+ * Replaces the per-spectrum scipy.sparse spsolve loop (baseline.py:27-37) by a batched banded LDL^T in float64, one thread
+ * per spectrum, with the reference's re-weighting w = p*(y > z) + (1-p)*(y < z) between the n_iter solves.
+ *   in_dev          [batch, n] complex64 (in_is_complex=1: the real part is used, baseline.py:84-85) or float32
+ *   out_dev         [batch, n] float32: real part minus its baseline (baseline.py:99)
+ *   workspace_dev   factor scratch, xmr_baseline_als_workspace_bytes(batch, n) bytes for full occupancy (any multiple of
+ *                   one CTA's share works: fewer CTAs run at a time) */
+int64_t xmr_baseline_als_workspace_bytes(int64_t batch, int n);
+int xmr_baseline_als(const void* in_dev, int in_is_complex, float* out_dev, int64_t batch, int n, double lam, double p,
+                     int n_iter, void* workspace_dev, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

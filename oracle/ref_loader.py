@@ -74,5 +74,6 @@ def load_reference():
     ns.fid = importlib.import_module("xmris.processing.fid")
     ns.phasing = importlib.import_module("xmris.processing.phasing")
     ns.bruker = importlib.import_module("xmris.vendor.bruker")      # remove_digital_filter ("next" row N4)
+    ns.baseline = importlib.import_module("xmris.processing.baseline")   # baseline_als (the step after autophase)
     _loaded = ns
     return ns

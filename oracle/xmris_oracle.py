@@ -326,6 +326,39 @@ def autophase_each(values, axis, coord, method="acme", peak_width=0.5, target_co
 
 
 # --------------------------------------------------------------------------------------------
+# "later" row  baseline_als                               reference: processing/baseline.py:10-119
+# --------------------------------------------------------------------------------------------
+
+
+def als_core(y, lam, p, n_iter):
+    """1-D asymmetric least squares baseline (``baseline.py:10-39``): the same scipy.sparse calls as the reference."""
+    from scipy import sparse
+    from scipy.sparse.linalg import spsolve
+
+    L = len(y)
+    D = sparse.diags([1, -2, 1], [0, 1, 2], shape=(L - 2, L), dtype=float)
+    D_T_D = (lam * D.T.dot(D)).tocsc()
+    w = np.ones(L)
+    z = None
+    for _ in range(n_iter):
+        W = sparse.diags(w, 0, format="csc", dtype=float)
+        z = spsolve(W + D_T_D, w * y)
+        w = p * (y > z) + (1 - p) * (y < z)
+    return z
+
+
+def baseline_als(values, axis, lam=1e5, p=0.001, n_iter=10):
+    """Real part minus its AsLS baseline along ``axis`` (``baseline.py:81-105``).  Returns ``(corrected, baseline)``."""
+    values = np.asarray(values)
+    work = np.real(values) if np.iscomplexobj(values) else values
+    moved = np.moveaxis(work, axis, -1)
+    flat = moved.reshape(-1, moved.shape[-1])
+    base = np.stack([als_core(row, lam, p, n_iter) for row in flat]).reshape(moved.shape)
+    base = np.moveaxis(base, -1, axis)
+    return work - base, base
+
+
+# --------------------------------------------------------------------------------------------
 # N4  remove_digital_filter                              reference: vendor/bruker.py:7-118
 # --------------------------------------------------------------------------------------------
 

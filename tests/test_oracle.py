@@ -198,3 +198,21 @@ def test_bruker_fixture_known_answer():
     assert abs(ppm - float(g["truth_ppm"])) <= df / float(g["real_f0"])
     allc, _ = orc.remove_digital_filter(g["real_fid"], 0, g["real_time"], float(g["real_gd"]), keep_length=True)
     assert np.array_equal(allc, g["real_all_clean"])
+
+
+# ---- baseline_als (processing/baseline.py), tests/golden/make_golden_baseline.py ------------------------------------------
+
+
+@pytest.mark.parametrize("tag,kw", [("a", dict(lam=1e5, p=0.01, n_iter=10)), ("b", dict(lam=1e5, p=0.001, n_iter=10)),
+                                    ("c", dict(lam=1e7, p=0.05, n_iter=4))])
+def test_baseline_als_matches_reference_bitwise(tag, kw):
+    g = load_golden("baseline")
+    corrected, base = orc.baseline_als(g["spec"], 2, **kw)
+    assert not np.iscomplexobj(corrected) and np.array_equal(corrected, g[f"corr_{tag}"])
+    assert np.array_equal(corrected + base, g["spec"].real) or np.allclose(corrected + base, g["spec"].real, rtol=1e-15)
+
+
+def test_baseline_als_middle_axis_and_real_input():
+    g = load_golden("baseline")
+    corrected, _ = orc.baseline_als(g["real_in"], 1, lam=1e6, p=0.001, n_iter=10)
+    assert np.array_equal(corrected, g["real_corr"])

@@ -62,6 +62,10 @@ class XmrisB200Accessor:
     def zero_fill(self, dim: str = DIMS.time, target_points: int = 1024, position: str = "end"):
         return P.zero_fill(self._obj, dim=dim, target_points=target_points, position=position)
 
+    # --- baseline (accessor.py:552-597) ---
+    def baseline_als(self, dim: str = DIMS.frequency, lam: float = 1e5, p: float = 0.001, n_iter: int = 10):
+        return P.baseline_als(self._obj, dim=dim, lam=lam, p=p, n_iter=n_iter)
+
     # --- phasing (accessor.py:599-683) ---
     def phase(self, dim: str = DIMS.frequency, p0: float = 0.0, p1: float = 0.0, pivot: float = None):
         return P.phase(self._obj, dim=dim, p0=p0, p1=p1, pivot=pivot)

@@ -393,6 +393,37 @@ def _workspace(device):
     return ws
 
 
+_als_workspaces: dict = {}
+
+
+def baseline_als(x, lam=1e5, p=0.001, n_iter=10, out=None, stream=None):
+    """Real part of ``x[..., n]`` (complex64 or float32 CUDA tensor) minus its asymmetric-least-squares baseline along the
+    last axis (``xmr_baseline_als``).  Returns a float32 tensor of the same shape."""
+    torch = _torch()
+    lib = _lib.load()
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise TypeError("x must be a CUDA torch tensor (xmris_b200 has no CPU path)")
+    if x.dtype not in (torch.complex64, torch.float32):
+        raise TypeError(f"baseline_als works on complex64 or float32 device tensors, got {x.dtype}")
+    x = x.contiguous()
+    n = x.shape[-1]
+    batch = x.numel() // max(n, 1)
+    if out is None:
+        out = torch.empty(tuple(x.shape), dtype=torch.float32, device=x.device)
+    need = int(lib.xmr_baseline_als_workspace_bytes(batch, int(n)))
+    key = (x.device.type, x.device.index)
+    ws = _als_workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = None
+        _als_workspaces.pop(key, None)                     # release the old one before growing
+        ws = torch.empty(max(need, 1), dtype=torch.uint8, device=x.device)
+        _als_workspaces[key] = ws
+    with torch.cuda.device(x.device):
+        _lib.check(lib.xmr_baseline_als(_ptr(x), int(x.dtype == torch.complex64), _ptr(out), batch, int(n), float(lam),
+                                        float(p), int(n_iter), _ptr(ws), int(ws.numel()), _stream_ptr(stream)))
+    return out
+
+
 _chain_workspaces: dict = {}
 
 

@@ -366,6 +366,37 @@ def to_hz(da, dim: str = DIMS.chemical_shift):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# baseline_als (the step after autophase)                          reference: processing/baseline.py:42-119
+# ---------------------------------------------------------------------------------------------------------
+
+
+def baseline_als(da, dim: str = DIMS.frequency, lam: float = 1e5, p: float = 0.001, n_iter: int = 10):
+    """Asymmetric least squares baseline correction of the REAL part along ``dim`` (``baseline.py:42-119``): every 1-D
+    spectrum gets ``n_iter`` re-weighted penalised solves ``(W + lam D'D) z = W y`` -- on the device, one thread per
+    spectrum (banded LDL^T in float64).  Returns the strictly real corrected spectrum (float32) with the reference's
+    lineage attrs; the input is not modified."""
+    _check_dims(da, dim, "baseline_als")
+    axis = da.get_axis_num(dim)
+    values = np.asarray(da.values)
+    import torch
+
+    moved = np.moveaxis(values, axis, -1)
+    if np.iscomplexobj(values):
+        x = torch.from_numpy(np.ascontiguousarray(moved, dtype=np.complex64)).to(_device())
+    else:
+        x = torch.from_numpy(np.ascontiguousarray(moved, dtype=np.float32)).to(_device())
+    corrected = D.baseline_als(x, lam=lam, p=p, n_iter=n_iter).cpu().numpy()
+    corrected = np.ascontiguousarray(np.moveaxis(corrected, -1, axis))
+    res = xr.DataArray(corrected, dims=da.dims, coords={k: da.coords[k] for k in da.coords}, name=da.name)
+    res.attrs = dict(da.attrs)
+    res.attrs[ATTRS.baseline_method] = "als"
+    res.attrs[ATTRS.baseline_lam] = lam
+    res.attrs[ATTRS.baseline_p] = p
+    res.attrs[ATTRS.baseline_iter] = n_iter
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------
 # data formats either side of the path                               reference: processing/utils.py:8-84
 # ---------------------------------------------------------------------------------------------------------
 # Storage formats without complex numbers (netCDF: the reference's Bruker fixtures) keep (real, imag) along a

@@ -32,6 +32,10 @@ class _Attrs:
     apodization_gb = XmrisTerm("apodization_gb", "Gaussian broadening factor applied.", "Hz")
     zero_fill_target = XmrisTerm("zero_fill_target", "Total number of points after zero-filling.")
     zero_fill_position = XmrisTerm("zero_fill_position", "Position of padding ('end' or 'symmetric').")
+    baseline_method = XmrisTerm("baseline_method", "The algorithm used to estimate and remove the spectral baseline.")
+    baseline_lam = XmrisTerm("baseline_lam", "The smoothness penalty (lambda) applied during AsLS baseline correction.")
+    baseline_p = XmrisTerm("baseline_p", "The asymmetry parameter applied during AsLS baseline correction.")
+    baseline_iter = XmrisTerm("baseline_iter", "The number of sparse solver iterations used to calculate the baseline.")
 
 
 class _Dims:

@@ -576,3 +576,26 @@ def register_dataset_accessor(name):
         return accessor
 
     return decorator
+
+
+def apply_ufunc(func, *args, kwargs=None, input_core_dims=None, output_core_dims=((),), vectorize=False, dask="forbidden",
+                **_ignored):
+    """The one calling pattern the reference uses (``processing/baseline.py:88-96``): a single DataArray argument, one
+    input and one output core dimension, ``vectorize=True`` -- ``func`` is applied to every 1-D slice along the core
+    dimension and, as in xarray, the core dimension ends up LAST in the result."""
+    if len(args) != 1 or not isinstance(args[0], DataArray):
+        raise NotImplementedError("xarray_lite.apply_ufunc supports a single DataArray argument")
+    da = args[0]
+    in_core = list((input_core_dims or [[]])[0])
+    out_core = list(list(output_core_dims)[0]) if output_core_dims else []
+    if len(in_core) != 1 or out_core != in_core or not vectorize:
+        raise NotImplementedError("xarray_lite.apply_ufunc supports one shared input/output core dimension with vectorize=True")
+    dim = in_core[0]
+    axis = da.get_axis_num(dim)
+    moved = np.moveaxis(np.asarray(da.values), axis, -1)
+    flat = moved.reshape(-1, moved.shape[-1])
+    out = np.stack([np.asarray(func(row, **(kwargs or {}))) for row in flat]) if len(flat) else flat.copy()
+    out = out.reshape(moved.shape[:-1] + (out.shape[-1],))
+    dims = tuple(d for d in da.dims if d != dim) + (dim,)
+    coords = {k: da.coords[k] for k in da.coords}
+    return DataArray(out, dims=dims, coords=coords, name=da.name)
