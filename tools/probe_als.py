@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from xmris_b200 import device as D
 dev = torch.device("cuda:0")
-for batch, n, it in [(65536, 1024, 10), (65536, 2048, 10), (65536, 4096, 10), (262144, 4096, 10)]:
+CASES = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]      # "batch,n,n_iter"
+for batch, n, it in CASES or [(65536, 1024, 10), (65536, 2048, 10), (65536, 4096, 10), (262144, 4096, 10), (1048576, 1024, 10)]:
     x = torch.randn(batch, n, device=dev).cumsum(dim=1).to(torch.complex64)
     out = torch.empty(batch, n, dtype=torch.float32, device=dev)
     ts = []

@@ -19,7 +19,8 @@
 namespace {
 
 constexpr int ALS_TPB = 128;             // spectra per CTA (one per thread)
-constexpr int ALS_MAX_CTAS_PER_SM = 8;
+constexpr int ALS_MAX_CTAS_PER_SM = 4;
+constexpr int ALS_U = 8;                 // points whose loads are in flight ahead of the recurrences
 
 struct AlsParams {
     const void* in;
@@ -79,39 +80,70 @@ __global__ void __launch_bounds__(ALS_TPB) als_kernel(const __grid_constant__ Al
             for (int it = 0; it < a.n_iter; ++it) {
                 const bool last = (it == a.n_iter - 1);
                 double d1 = 0.0, d2 = 0.0, l1 = 0.0, l2 = 0.0, l2n = 0.0, u1 = 0.0, u2 = 0.0;   // l1 = l1_i, l2 = l2_i, l2n = l2_{i+1}
-                for (int i = 0; i < n; ++i) {
-                    const size_t o = size_t(i) * ALS_TPB + tid;
-                    const double y = double(Y[o]);
-                    double w = 1.0;                                   // baseline.py:24: the first solve is unweighted
-                    if (it > 0) {
-                        const unsigned char c = W[o];
-                        w = c == 1 ? pw : (c == 2 ? qw : 0.0);
+                // Both sweeps are latency chains per thread; their loads do not depend on the chain, so they are issued
+                // ALS_U points ahead of it (the kernel is bound by HBM latency x bytes in flight).
+                for (int ib = 0; ib < n; ib += ALS_U) {
+                    float yv[ALS_U];
+                    unsigned char cv[ALS_U];
+#pragma unroll
+                    for (int k = 0; k < ALS_U; ++k) {
+                        const int i = ib + k;
+                        const size_t o = size_t(i < n ? i : n - 1) * ALS_TPB + tid;
+                        yv[k] = Y[o];
+                        cv[k] = it > 0 ? W[o] : (unsigned char)3;
                     }
-                    // bands of D'D (D = second differences, (n-2) x n): rows k = i, i-1, i-2 of D touch column i
-                    const int v0 = (i <= n - 3), v1 = (i >= 1 && i <= n - 2), v2 = (i >= 2);
-                    const double dg = double(v0 + 4 * v1 + v2);
-                    const double o1 = (i <= n - 2) ? -2.0 * double(v0 + v1) : 0.0;      // (i, i+1)
-                    const double o2 = v0 ? 1.0 : 0.0;                                    // (i, i+2)
-                    const double d = (w + lam * dg) - l1 * l1 * d1 - l2 * l2 * d2;
-                    const double u = w * y - l1 * u1 - l2 * u2;
-                    const double dinv = 1.0 / d;
-                    const double q = (lam * o1 - l2n * l1 * d1) * dinv;                  // l1_{i+1}
-                    const double pp = (lam * o2) * dinv;                                 // l2_{i+2}
-                    Q[o] = q;
-                    P[o] = pp;
-                    V[o] = u * dinv;
-                    d2 = d1; d1 = d; u2 = u1; u1 = u;
-                    l2 = l2n; l1 = q; l2n = pp;
+#pragma unroll
+                    for (int k = 0; k < ALS_U; ++k) {
+                        const int i = ib + k;
+                        if (i < n) {
+                            const size_t o = size_t(i) * ALS_TPB + tid;
+                            const double y = double(yv[k]);
+                            const unsigned char c = cv[k];
+                            const double w = c == 3 ? 1.0 : (c == 1 ? pw : (c == 2 ? qw : 0.0));   // baseline.py:24: first solve unweighted
+                            // bands of D'D (D = second differences, (n-2) x n): rows k = i, i-1, i-2 of D touch column i
+                            const int v0 = (i <= n - 3), v1 = (i >= 1 && i <= n - 2), v2 = (i >= 2);
+                            const double dg = double(v0 + 4 * v1 + v2);
+                            const double o1 = (i <= n - 2) ? -2.0 * double(v0 + v1) : 0.0;      // (i, i+1)
+                            const double o2 = v0 ? 1.0 : 0.0;                                    // (i, i+2)
+                            const double d = (w + lam * dg) - l1 * l1 * d1 - l2 * l2 * d2;
+                            const double u = w * y - l1 * u1 - l2 * u2;
+                            const double dinv = 1.0 / d;
+                            const double q = (lam * o1 - l2n * l1 * d1) * dinv;                  // l1_{i+1}
+                            const double pp = (lam * o2) * dinv;                                 // l2_{i+2}
+                            Q[o] = q;
+                            P[o] = pp;
+                            V[o] = u * dinv;
+                            d2 = d1; d1 = d; u2 = u1; u1 = u;
+                            l2 = l2n; l1 = q; l2n = pp;
+                        }
+                    }
                 }
                 double z1 = 0.0, z2 = 0.0;
-                for (int i = n - 1; i >= 0; --i) {
-                    const size_t o = size_t(i) * ALS_TPB + tid;
-                    const double z = V[o] - Q[o] * z1 - P[o] * z2;
-                    const double y = double(Y[o]);
-                    if (last) Y[o] = float(y - z);                                       // baseline.py:99: corrected = real - baseline
-                    else W[o] = y > z ? 1 : (y < z ? 2 : 0);                             // baseline.py:37
-                    z2 = z1;
-                    z1 = z;
+                for (int ib = n - 1; ib >= 0; ib -= ALS_U) {
+                    double vv[ALS_U], qv[ALS_U], pv[ALS_U];
+                    float yv[ALS_U];
+#pragma unroll
+                    for (int k = 0; k < ALS_U; ++k) {
+                        const int i = ib - k;
+                        const size_t o = size_t(i >= 0 ? i : 0) * ALS_TPB + tid;
+                        vv[k] = V[o];
+                        qv[k] = Q[o];
+                        pv[k] = P[o];
+                        yv[k] = Y[o];
+                    }
+#pragma unroll
+                    for (int k = 0; k < ALS_U; ++k) {
+                        const int i = ib - k;
+                        if (i >= 0) {
+                            const size_t o = size_t(i) * ALS_TPB + tid;
+                            const double z = vv[k] - qv[k] * z1 - pv[k] * z2;
+                            const double y = double(yv[k]);
+                            if (last) Y[o] = float(y - z);                                       // baseline.py:99: corrected = real - baseline
+                            else W[o] = y > z ? 1 : (y < z ? 2 : 0);                             // baseline.py:37
+                            z2 = z1;
+                            z1 = z;
+                        }
+                    }
                 }
             }
         }
