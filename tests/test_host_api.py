@@ -43,10 +43,11 @@ def test_reference_dim_defaults_table():
             ("to_spectrum", "out_dim", "frequency"), ("to_fid", "dim", "frequency"), ("to_fid", "out_dim", "time"),
             ("zero_fill", "dim", "time"), ("autophase", "dim", "frequency"), ("remove_digital_filter", "dim", "time"),
             ("to_ppm", "dim", "frequency"), ("to_hz", "dim", "chemical_shift"), ("to_real_imag", "dim", "component"),
-            ("to_complex", "dim", "component")]
+            ("to_complex", "dim", "component"), ("baseline_als", "dim", "frequency")]
     for method, param, want in rows:
         assert inspect.signature(getattr(XmrisB200Accessor, method)).parameters[param].default == want, (method, param)
     assert _defaults(XmrisB200Accessor.remove_digital_filter) == {"dim": "time", "keep_length": True}
+    assert _defaults(XmrisB200Accessor.baseline_als) == {"dim": "frequency", "lam": 1e5, "p": 0.001, "n_iter": 10}   # accessor.py:552-558
 
 
 def test_real_imag_round_trip_known_answer():
