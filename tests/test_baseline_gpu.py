@@ -43,6 +43,13 @@ def test_baseline_als_matches_reference(xm, tag, kw):
                        "baseline_p": full["p"], "baseline_iter": full["n_iter"]}
     assert np.iscomplexobj(da.values) and np.array_equal(da.values, g["spec"])          # input untouched
     np.testing.assert_array_equal(r.coords["frequency"].values, g["freq"])
+    # the same on a device-resident complex64 tensor (the kernel takes the real part itself)
+    import torch
+    from xmris_b200 import device as D
+
+    full.pop("n_iter")
+    dev_out = D.baseline_als(torch.from_numpy(g["spec"].astype(np.complex64)).cuda(), n_iter=kw.get("n_iter", 10), **full)
+    assert np.array_equal(dev_out.cpu().numpy(), r.values)
 
 
 def test_baseline_als_middle_axis_real_input_and_errors(xm):

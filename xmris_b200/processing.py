@@ -382,9 +382,8 @@ def baseline_als(da, dim: str = DIMS.frequency, lam: float = 1e5, p: float = 0.0
 
     moved = np.moveaxis(values, axis, -1)
     if np.iscomplexobj(values):
-        x = torch.from_numpy(np.ascontiguousarray(moved, dtype=np.complex64)).to(_device())
-    else:
-        x = torch.from_numpy(np.ascontiguousarray(moved, dtype=np.float32)).to(_device())
+        moved = moved.real                      # baseline.py:84-85: only the real part travels to the device
+    x = torch.from_numpy(np.ascontiguousarray(moved, dtype=np.float32)).to(_device())
     corrected = D.baseline_als(x, lam=lam, p=p, n_iter=n_iter).cpu().numpy()
     corrected = np.ascontiguousarray(np.moveaxis(corrected, -1, axis))
     res = xr.DataArray(corrected, dims=da.dims, coords={k: da.coords[k] for k in da.coords}, name=da.name)
