@@ -355,6 +355,31 @@ def run_ours(args):
                      "what": "same chain with autophase mode='all' (one fused kernel per voxel: FFT + in-CTA (p0,p1) search + "
                              "phase); SFU/FP32-bound, see DESIGN.md K2"}
 
+    # ---- the step after the chain in the reference's pipeline: baseline_als on the phased spectra (kernel K3) ----------
+    als = None
+    if args.mode == "single" and not args.no_per_voxel and rank == 0:
+        from xmris_b200 import device as D
+
+        nb = min(batch, args.per_voxel_batch)
+        als_out = torch.empty((nb, n), dtype=torch.float32, device=dev)
+        D.baseline_als(out[:nb], out=als_out)
+        torch.cuda.synchronize()
+        ae0, ae1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ae0.record()
+        for _ in range(2):
+            D.baseline_als(out[:nb], out=als_out)
+        ae1.record()
+        torch.cuda.synchronize()
+        als_ms = ae0.elapsed_time(ae1) / 2
+        als_bytes = (58.0 * n * 10 + 20.0 * n) * nb
+        als = {"value": nb / (als_ms / 1e3), "unit": "spectra/s", "voxels": nb, "ms": als_ms, "n_iter": 10,
+               "gbs": als_bytes / (als_ms / 1e3) / 1e9, "algorithmic_bytes": als_bytes,
+               "what": "baseline_als (lam=1e5, p=0.001, 10 iterations) on the phased spectra of one GPU: batched banded "
+                       "LDL^T in float64, HBM-bound on 58 B/point/iteration of factor scratch; see DESIGN.md K3"}
+        del als_out
+        D._als_workspaces.clear()
+        torch.cuda.empty_cache()
+
     # ---- e2e: pinned host buffers, H2D + chain + D2H inside the timed region ---------------------------------
     e2e = None
     if not args.no_e2e:
@@ -442,6 +467,8 @@ def run_ours(args):
     if args.mode == "single" and os.path.isfile(tpath):
         tj = json.load(open(tpath))    # bytes/spectrum from the committed ncu --set full capture, scaled to this launch
         traffic = (tj["dram_bytes_read_per_spectrum"] + tj["dram_bytes_write_per_spectrum"]) * batch
+    if als is not None:
+        als["frac_of_hbm_peak"] = als["gbs"] / peak
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "algorithmic_bytes": b_alg, "kernel": dominant, "kernel_ms": dom_ms, "peak_source": peak_src,
                 "chain_achieved": chain_achieved, "chain_frac": chain_achieved / peak,
@@ -462,7 +489,7 @@ def run_ours(args):
         "config": {"workload": f"C5: {batch} voxels x {n}-pt FID per GPU -> {n}-pt spectrum, lb={LB}, full chain "
                                f"zero_fill(no-op)->apodize_exp->to_spectrum->autophase(mode={args.mode}, acme)",
                    "l2": "inputs (32 GiB/GPU) far exceed the 126 MB L2; no explicit flush", "autophase_mode": args.mode},
-        "roofline": roofline, "breakdown_ms": breakdown, "per_voxel": per_voxel, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches["n"], "clocks": clocks,
+        "roofline": roofline, "breakdown_ms": breakdown, "per_voxel": per_voxel, "baseline_als": als, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches["n"], "clocks": clocks,
         "result": {"p0": last[0], "p1": last[1], "pivot": last[2]} if args.mode == "single" else None,
     }
     emit(line)
