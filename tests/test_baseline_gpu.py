@@ -96,3 +96,21 @@ def test_baseline_notebook_known_answer_and_ragged_batches(xm):
         want, _ = orc.baseline_als(x.astype(np.float64), 1, lam=1e3, p=0.02, n_iter=6)
         got = D.baseline_als(torch.from_numpy(x).cuda(), lam=1e3, p=0.02, n_iter=6).cpu().numpy()
         assert np.linalg.norm(got - want) <= TOL * max(np.linalg.norm(want), np.linalg.norm(x)), (batch, m)
+
+
+def test_process_fid_with_baseline_equals_chained_calls(xm):
+    """The fused entry point with ``baseline_kwargs`` (spectrum stays on the device) gives what the chained accessor calls
+    give: same values, dims, coords and lineage attrs."""
+    from xmris_b200.synth import make_fids_numpy
+
+    fid, t, _ = make_fids_numpy("1H", 24, 1024, seed=21)
+    da = xm.xr.DataArray(fid.reshape(4, 6, 1024).astype(np.complex64), dims=["y", "x", "time"], coords={"time": t},
+                         attrs={"reference_frequency": 127.6, "carrier_ppm": 4.7})
+    fused = da.xmr.process_fid(target_points=2048, lb=5.0, autophase_kwargs=dict(peak_width=100),
+                               baseline_kwargs=dict(lam=1e4, p=0.01))
+    chained = (da.xmr.zero_fill(target_points=2048).xmr.apodize_exp(lb=5.0).xmr.to_spectrum()
+               .xmr.autophase(peak_width=100).xmr.baseline_als(lam=1e4, p=0.01))
+    assert fused.dims == chained.dims and not np.iscomplexobj(fused.values)
+    assert rel_l2(fused.values, chained.values) <= TOL
+    assert fused.attrs == chained.attrs
+    np.testing.assert_array_equal(fused.coords["frequency"].values, chained.coords["frequency"].values)

@@ -90,9 +90,10 @@ class XmrisB200Accessor:
 
     # --- fused chain (B200 extension) ---
     def process_fid(self, dim: str = DIMS.time, out_dim: str = DIMS.frequency, target_points: int | None = None,
-                    position: str = "end", lb: float | None = None, autophase_kwargs: dict | None = None):
+                    position: str = "end", lb: float | None = None, autophase_kwargs: dict | None = None,
+                    baseline_kwargs: dict | None = None):
         return P.process_fid(self._obj, dim=dim, out_dim=out_dim, target_points=target_points, position=position,
-                             lb=lb, autophase_kwargs=autophase_kwargs)
+                             lb=lb, autophase_kwargs=autophase_kwargs, baseline_kwargs=baseline_kwargs)
 
 
 def register():

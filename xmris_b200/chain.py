@@ -189,8 +189,11 @@ def chain_to_spectrum(fid_t, time_coord, target_points=None, position="end", lb=
     return spec, geo["freqs"], geo
 
 
-def run_chain_dataarray(da, dim, out_dim, target_points, position, lb, autophase_kwargs):
-    """DataArray front end of the fused chain: same coords / attrs / lineage as the chained accessor calls."""
+def run_chain_dataarray(da, dim, out_dim, target_points, position, lb, autophase_kwargs, baseline_kwargs=None):
+    """DataArray front end of the fused chain: same coords / attrs / lineage as the chained accessor calls.
+
+    ``baseline_kwargs`` (``lam, p, n_iter``): additionally run ``baseline_als`` on the device-resident spectrum (the step
+    after autophase in the reference's pipeline); the result is then real-valued."""
     from . import processing as P
     from ._xr import xr
 
@@ -211,7 +214,7 @@ def run_chain_dataarray(da, dim, out_dim, target_points, position, lb, autophase
             name = None
     target = out_dim if out_dim is not None else dim
     n_out_chk = int(target_points) if padded else n_in
-    use_host_abi = n_out_chk in D.SUPPORTED_N and (autophase_kwargs is None or (
+    use_host_abi = baseline_kwargs is None and n_out_chk in D.SUPPORTED_N and (autophase_kwargs is None or (
         autophase_kwargs.get("lb", 0.0) == 0.0 and (autophase_kwargs.get("mode", "single") != "all" or n_out_chk >= 512)))
     if use_host_abi:
         # numpy in -> ONE C-ABI call on host buffers -> numpy out (no torch on this path)
@@ -248,6 +251,11 @@ def run_chain_dataarray(da, dim, out_dim, target_points, position, lb, autophase
     coords[target] = var
     if spec is None:
         values = np.ascontiguousarray(np.moveaxis(out_np, -1, axis)).astype(P.OUTPUT_DTYPE, copy=False)
+    elif baseline_kwargs is not None:
+        bk = dict(lam=1e5, p=0.001, n_iter=10)
+        bk.update(baseline_kwargs)
+        real = D.baseline_als(spec, lam=bk["lam"], p=bk["p"], n_iter=bk["n_iter"])       # the spectrum never left the device
+        values = np.ascontiguousarray(np.moveaxis(real.cpu().numpy(), -1, axis))
     else:
         values = P._from_device(spec, axis)
     res = xr.DataArray(values, dims=dims, coords=coords, attrs=attrs, name=name)
@@ -263,4 +271,9 @@ def run_chain_dataarray(da, dim, out_dim, target_points, position, lb, autophase
         from .pervoxel import attach_per_spectrum_coords
 
         res = attach_per_spectrum_coords(res, target, info)
+    if baseline_kwargs is not None:
+        res.attrs[ATTRS.baseline_method] = "als"
+        res.attrs[ATTRS.baseline_lam] = bk["lam"]
+        res.attrs[ATTRS.baseline_p] = bk["p"]
+        res.attrs[ATTRS.baseline_iter] = bk["n_iter"]
     return res
