@@ -54,48 +54,76 @@ def parse():
 
 
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU while the timed region runs: NVML polled from a thread every 2 ms
+    (`nvidia-smi -lms` through a pipe is block-buffered and loses the samples of a sub-second region); falls back to
+    single `nvidia-smi` queries when NVML cannot be loaded."""
+
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.first, self.alive, self.thread, self.how = index, [], 0, False, None, None
+
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+        return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+            nv, h = self._nvml_handle()
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            def poll():
+                while self.alive:
+                    try:
+                        self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), mx, int(reasons_fn(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+
+            self.how = "nvml"
+        except Exception:
+            def poll():
+                while self.alive:
+                    try:
+                        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                              "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                        r = [c.strip() for c in out.strip().split(",")]
+                        mask = sum(bit for (bit, _), col in zip(self.REASONS, (4, 5, 6, 7))
+                                   if len(r) > col and r[col].lower().startswith("active"))
+                        self.rows.append((float(r[1]), float(r[2]), mask))
+                    except Exception:
+                        time.sleep(0.05)
+
+            self.how = "nvidia-smi"
+        self.alive = True
+        self.thread = threading.Thread(target=poll, daemon=True)
+        self.thread.start()
 
     def mark(self):
         """Index of the next sample: call at the start of the timed region (the sampler is started before warm-up)."""
         self.first = len(self.rows)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.05)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        rows = self.rows[getattr(self, "first", 0):] or self.rows[-1:]
+        self.alive = False
+        if self.thread is not None:
+            self.thread.join(timeout=6)
+        rows = self.rows[self.first:] or self.rows[-1:]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"],
+                    "samples": 0}
+        mask = 0
         for r in rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6), ("sw_power_cap", 7)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            mask |= r[2]
+        return {"sm_mhz": float(np.median([r[0] for r in rows])), "sm_max_mhz": max(r[1] for r in rows),
+                "reasons": sorted(name for bit, name in self.REASONS if mask & bit), "samples": len(rows), "source": self.how}
 
 
 # ---------------------------------------------------------------------------------------------------------
