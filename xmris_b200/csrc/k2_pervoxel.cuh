@@ -33,6 +33,10 @@ constexpr int K2_NP1 = 179;      // coarse p1: -4000 + 45*k (last clamped to 400
 #endif
 constexpr int K2_NSTART = XMR_K2_NSTART;
 constexpr int K2_NROUND = 7;
+#ifndef XMR_K2_SHRINK
+#define XMR_K2_SHRINK 0.32f
+#endif
+constexpr float K2_SHRINK = XMR_K2_SHRINK;   // window half-width ratio between zoom rounds (8 points per axis: spacing = 2h/7)
 constexpr int K2_NSHORT = 64;     // coarse cells re-evaluated at the finer subsample
 constexpr int K2_NP0_ONLY = 121; // p0_only coarse: -180 + 3*k
 constexpr int K2_PPL_SHIFT = 5;   // log2(pairs per lane) for N = 4096; other N: any padding works, 4096 is conflict-free
@@ -533,8 +537,8 @@ k2_kernel(const __grid_constant__ K2Params p) {
                 }
                 st_f[t] = bf; st_p0[t] = b0; st_p1[t] = b1;
             }
-            h0 *= 0.32f;
-            h1 *= 0.32f;
+            h0 *= K2_SHRINK;
+            h1 *= K2_SHRINK;
             __syncthreads();
         }
         float fin_f = CUDART_INF_F, fin_p0 = 0.f, fin_p1 = 0.f;
