@@ -262,3 +262,24 @@ def test_to_ppm_to_hz_coordinates_only():
         xr.DataArray(np.zeros(3), dims=["frequency"], coords={"frequency": np.arange(3.0)}).xmr.to_ppm()
     with pytest.raises(ValueError, match="missing dimension"):
         da.xmr.to_ppm(dim="nope")
+
+
+def test_chain_geometry_is_memoised_and_read_only():
+    from xmris_b200 import chain
+
+    t = np.arange(1024) / 5000.0
+    a = chain.chain_geometry(1024, t, 2048, "end", 5.0)
+    b = chain.chain_geometry(1024, t.copy(), 2048, "end", 5.0)
+    assert a is b and a["n_out"] == 2048 and a["pad_left"] == 0
+    for key in ("t_pad", "window", "freqs"):
+        assert not a[key].flags.writeable                      # shared by every caller: must not be modified in place
+    c = chain.chain_geometry(1024, t, 2048, "symmetric", 5.0)
+    d = chain.chain_geometry(1024, t + 1e-6, 2048, "end", 5.0)
+    assert c is not a and c["pad_left"] == 512 and d is not a
+    # float64 tables as the reference builds them (fid.py:136 with the ortho norm, fourier.py:95, 31-32)
+    t_pad = t[0] + np.arange(2048) * (t[1] - t[0])                # fid.py:254-263: the padded axis is rebuilt from c0 and delta
+    np.testing.assert_array_equal(a["t_pad"], t_pad)
+    np.testing.assert_array_equal(a["window"], np.exp(-np.pi * 5.0 * t_pad) / np.sqrt(2048))
+    np.testing.assert_array_equal(a["freqs"], np.roll(np.fft.fftfreq(2048, d=t[1] - t[0]), 1024))
+    with pytest.raises(ValueError, match="position"):
+        chain.chain_geometry(1024, t, 2048, "middle", 5.0)
