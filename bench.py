@@ -405,7 +405,6 @@ def run_ours(args):
                "what": "baseline_als (lam=1e5, p=0.001, 10 iterations) on the phased spectra of one GPU: batched banded "
                        "LDL^T in float64, HBM-bound on 58 B/point/iteration of factor scratch; see DESIGN.md K3"}
         del als_out
-        D._als_workspaces.clear()
         torch.cuda.empty_cache()
 
     # ---- e2e: pinned host buffers, H2D + chain + D2H inside the timed region ---------------------------------

@@ -394,6 +394,7 @@ def _workspace(device):
 
 
 _als_workspaces: dict = {}
+_ALS_KEEP_BYTES = 256 << 20
 
 
 def baseline_als(x, lam=1e5, p=0.001, n_iter=10, out=None, stream=None):
@@ -414,10 +415,13 @@ def baseline_als(x, lam=1e5, p=0.001, n_iter=10, out=None, stream=None):
     key = (x.device.type, x.device.index)
     ws = _als_workspaces.get(key)
     if ws is None or ws.numel() < need:
-        ws = None
-        _als_workspaces.pop(key, None)                     # release the old one before growing
+        # the factor scratch can reach many GB (9 GB at n = 4096 with every SM busy): only small ones are kept between
+        # calls, large ones go back to torch's allocator when this call returns
         ws = torch.empty(max(need, 1), dtype=torch.uint8, device=x.device)
-        _als_workspaces[key] = ws
+        if need <= _ALS_KEEP_BYTES:
+            _als_workspaces[key] = ws
+        elif stream is not None and hasattr(stream, "cuda_stream"):
+            ws.record_stream(stream)          # freed on return: keep the allocator from reusing it before the kernel is done
     with torch.cuda.device(x.device):
         _lib.check(lib.xmr_baseline_als(_ptr(x), int(x.dtype == torch.complex64), _ptr(out), batch, int(n), float(lam),
                                         float(p), int(n_iter), _ptr(ws), int(ws.numel()), _stream_ptr(stream)))
