@@ -354,7 +354,11 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
 #pragma unroll
                 for (int d = 0; d < C::R2; ++d) {
                     const int k = t + C::T * j + Q * d;
-                    const int m = (k + out_shift) & (C::N - 1);
+                    // fast variants (out_shift == N/2): T*j + Q*d is a compile-time multiple of T and t < T never crosses
+                    // N/2, so the wrap is decided at compile time and every store address is `dst + t + immediate`
+                    constexpr int NH = C::N / 2;
+                    const int kc = C::T * j + Q * d;
+                    const int m = F ? t + (kc >= NH ? kc - NH : kc + NH) : ((k + out_shift) & (C::N - 1));
                     float2 x = v[j * C::R2 + d];
                     if (FOLD) {
                         x = cmul(x, p.ph_fold[d]);
