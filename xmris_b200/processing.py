@@ -1,7 +1,8 @@
 """Host-side mirror of the reference's hot-path functions ("xarray in, xarray out"), computing on the B200.
 
 Same names, arguments, defaults, error behaviour, dims/coords/attrs handling and lineage stamps as
-``src/xmris/processing/{fid,fourier,phasing}.py`` of andrewendlinger/xmris v0.6.1; the arithmetic runs in
+``src/xmris/processing/{fid,fourier,phasing,baseline,utils}.py`` and ``vendor/bruker.py:remove_digital_filter`` of
+andrewendlinger/xmris v0.6.1; the arithmetic runs in
 ``libxmris_b200.so`` (sm_100a CUDA) through :mod:`xmris_b200.device`.  Metadata (coordinates, attrs) is plain
 float64 numpy on the host exactly as in the reference.  There is no CPU fallback for the data path.
 
@@ -10,7 +11,9 @@ Deliberate differences (DESIGN.md "Deviations"):
   * ``autophase(mode="all")`` is implemented (per-spectrum search) where the reference raises NotImplementedError;
   * the optimiser is a deterministic grid + refinement instead of seeded differential evolution (same objective,
     same box bounds) -- it reproduces the reference's angles to well within 0.1 degree on well-posed spectra;
-  * transform lengths are powers of two in [16, 8192]; anything else raises ``ValueError``.
+  * transform lengths: powers of two in [16, 8192] on the fused kernels, any other length up to 4096 through a chirp-z
+    composition of them (e.g. the 1972-point Bruker FIDs); longer non-power-of-two lengths raise ``ValueError``;
+  * ``baseline_als`` returns float32 (float64 solves on the device).
 """
 
 from __future__ import annotations
