@@ -122,8 +122,22 @@ int64_t xmr_autophase_workspace_bytes(void);
  * Defaults: 6, 15, 4, 4, 2, 2, 2.5 (final spacing 0.01 x 0.024 deg). */
 int xmr_autophase_search_tuning(double p0_step_deg, double p1_step_deg, int starts, int levels, int f32_levels,
                                 int late_starts, double first_ratio);
+/* ACME only: how many mutually distinct basins of the last float32 zoom level are finished by the float64 Newton polish on the
+ * analytic gradient of the objective (default 3; 0 = the float64 zoom levels of `levels` instead).  The polish converges
+ * to the local minimum to ~1e-4 deg -- where the reference's own optimiser lands when run to convergence. */
+int xmr_autophase_search_polish(int starts);
 int xmr_autophase_search_c64(const void* spec_dev, int n, double u0, double du, int method, int target_idx,
                              int index_width, int p0_only, double* result_dev, void* workspace_dev, void* stream);
+
+/* The autophase objective itself at k given candidates -- what the searches minimise, exposed so that it can be checked
+ * against the reference's own score functions: _acme_score (src/xmris/processing/phasing.py:100-122),
+ * _peak_minima_score (:125-139), _roi_positivity_score (:142-157).  Arguments as xmr_autophase_search_c64;
+ *   p0_dev, p1_dev  double[k] degrees (device); out_dev double[k] objective values (device)
+ *   use_f64         1: float64 accumulation (the searches' final levels); 0: float32 (their coarse levels)
+ * Returns the reference's formula as written, including ACME's negative branch max(Re) <= 0 that the searches reject. */
+int xmr_autophase_score_c64(const void* spec_dev, int n, double u0, double du, int method, int target_idx,
+                            int index_width, const double* p0_dev, const double* p1_dev, int k, int use_f64,
+                            double* out_dev, void* stream);
 
 /* The whole chain per voxel in ONE pass (autophase mode="all"; the reference's NotImplementedError branch,
  * phasing.py:219-222, defined as "the reference's autophase applied to every 1-D spectrum on its own"):

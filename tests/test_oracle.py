@@ -88,6 +88,21 @@ def test_to_spectrum_known_answer():
     np.testing.assert_allclose(tb, t, atol=1e-12)
 
 
+def test_apodize_lg_matches_reference():
+    # reference fid.py:147-198 run by tests/golden/make_golden_lg.py; known answer docs/notebooks/pipeline/apodization.md:227-251
+    g = load_golden("apodize_lg")
+    t, fid = g["kat_time"], g["kat_fid"]
+    t_g = (2 * np.sqrt(np.log(2))) / (np.pi * 4.0)
+    np.testing.assert_allclose(g["kat_out"], fid * (np.exp(np.pi * 3.0 * t) * np.exp(-(t**2) / (t_g**2))))
+    np.testing.assert_array_equal(orc.apodize_lg(fid, 0, t, 3.0, 4.0), g["kat_out"])
+    np.testing.assert_array_equal(orc.apodize_lg(g["blk"], 1, g["blk_time"], 2.5, 6.0), g["blk_out"])
+    np.testing.assert_array_equal(orc.apodize_lg(g["blk"], 1, g["blk_time"], 2.5, 0.0), g["blk_gb0"])
+    zf, tz, _ = orc.zero_fill(g["chain_fid"], 1, t, 2048, "end")
+    sp, fr = orc.to_spectrum(orc.apodize_lg(zf, 1, tz, 4.0, 7.0), 1, tz)
+    np.testing.assert_array_equal(sp, g["chain_spec"])
+    np.testing.assert_array_equal(fr, g["chain_freq"])
+
+
 def test_phase_inverse_and_pivot_stability():
     # docs/notebooks/pipeline/phase.md:127-150
     g = load_golden("scores")

@@ -91,9 +91,21 @@ class XmrisB200Accessor:
     # --- fused chain (B200 extension) ---
     def process_fid(self, dim: str = DIMS.time, out_dim: str = DIMS.frequency, target_points: int | None = None,
                     position: str = "end", lb: float | None = None, autophase_kwargs: dict | None = None,
-                    baseline_kwargs: dict | None = None):
+                    baseline_kwargs: dict | None = None, gb: float | None = None):
         return P.process_fid(self._obj, dim=dim, out_dim=out_dim, target_points=target_points, position=position,
-                             lb=lb, autophase_kwargs=autophase_kwargs, baseline_kwargs=baseline_kwargs)
+                             lb=lb, autophase_kwargs=autophase_kwargs, baseline_kwargs=baseline_kwargs, gb=gb)
+
+    # --- everything this package does not rebuild (plot, widget, fit_amares, ...) -------------------------------------
+    _fallback_cls = None   # the accessor class that owned ".xmr" before register() (the reference's, when it is installed)
+
+    def __getattr__(self, name):
+        # only reached for attributes this class does not define: hand them to the accessor we displaced, so that importing
+        # xmris_b200 next to the reference does not make .xmr.plot / .xmr.widget / .xmr.fit_amares disappear
+        fb = type(self)._fallback_cls
+        if fb is not None and not name.startswith("__"):
+            return getattr(fb(self._obj), name)
+        raise AttributeError(f"{type(self).__name__!s} has no attribute {name!r} (not on the FID->spectrum hot path; "
+                             "install the reference package for plotting / fitting)")
 
 
 def register():
@@ -106,5 +118,9 @@ def register():
         warnings.simplefilter("ignore")
         xarray_lite.register_dataarray_accessor("xmr")(XmrisB200Accessor)
         if HAVE_XARRAY:  # pragma: no cover
+            prev = xr.DataArray.__dict__.get("xmr")
+            prev_cls = getattr(prev, "_accessor", None)
+            if prev_cls is not None and prev_cls is not XmrisB200Accessor:
+                XmrisB200Accessor._fallback_cls = prev_cls      # keep the displaced accessor reachable (see __getattr__)
             xr.register_dataarray_accessor("xmr")(XmrisB200Accessor)
     return XmrisB200Accessor

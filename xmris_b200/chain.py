@@ -14,6 +14,8 @@ never written.  Multi-GPU: each rank runs pass 1 on its shard, the (max, index) 
 
 from __future__ import annotations
 
+import threading
+
 import numpy as np
 
 from . import device as D
@@ -21,27 +23,30 @@ from .vocab import ATTRS, COORDS, DIMS
 
 
 _GEO_CACHE: dict = {}
+_GEO_LOCK = threading.RLock()     # the cache and the per-geometry "_prepared" / "_search" entries are shared by threads
 
 
-def chain_geometry(n_in, time_coord, target_points, position, lb):
+def chain_geometry(n_in, time_coord, target_points, position, lb, gb=None):
     """Host metadata of the chain: padded time axis, window (incl. 1/sqrt(N)), frequency axis, pad_left.
 
-    Memoised on the exact time coordinate (a repeated call on the same axis reuses the float64 tables and the window
+    ``gb`` given: the Lorentz-to-Gauss window of ``apodize_lg`` (``exp(+pi*lb*t) * exp(-t^2/t_g^2)``, fid.py:176-193) instead
+    of ``apodize_exp``'s ``exp(-pi*lb*t)`` (fid.py:136).  Memoised on the exact time coordinate (a repeated call on the same axis reuses the float64 tables and the window
     already uploaded to the device: for small batches these host steps cost more than the kernels)."""
     t = np.ascontiguousarray(time_coord, dtype=np.float64)
     key = (int(n_in), None if target_points is None else int(target_points), position, None if lb is None else float(lb),
-           t.tobytes())
-    hit = _GEO_CACHE.get(key)
-    if hit is not None:
-        return hit
-    geo = _chain_geometry(n_in, t, target_points, position, lb)
-    if len(_GEO_CACHE) >= 32:
-        _GEO_CACHE.pop(next(iter(_GEO_CACHE)))
-    _GEO_CACHE[key] = geo
-    return geo
+           None if gb is None else float(gb), t.tobytes())
+    with _GEO_LOCK:
+        hit = _GEO_CACHE.get(key)
+        if hit is not None:
+            return hit
+        geo = _chain_geometry(n_in, t, target_points, position, lb, gb)
+        if len(_GEO_CACHE) >= 32:
+            _GEO_CACHE.pop(next(iter(_GEO_CACHE)))
+        _GEO_CACHE[key] = geo
+        return geo
 
 
-def _chain_geometry(n_in, t, target_points, position, lb):
+def _chain_geometry(n_in, t, target_points, position, lb, gb=None):
     n_out, pad_left = n_in, 0
     t_pad = t
     if target_points is not None and target_points > n_in:
@@ -57,7 +62,13 @@ def _chain_geometry(n_in, t, target_points, position, lb):
         t_pad = (t[0] - pad_left * delta) + np.arange(n_out) * delta   # fid.py:254-263
     D.check_length(n_out)
     window = None
-    if lb is not None:
+    if gb is not None:
+        w = np.exp(np.pi * (1.0 if lb is None else lb) * t_pad)          # fid.py:176-193 (apodize_lg's default lb is 1.0)
+        if gb != 0:
+            t_g = (2 * np.sqrt(np.log(2))) / (np.pi * gb)
+            w = w * np.exp(-(t_pad**2) / (t_g**2))
+        window = w / np.sqrt(n_out)
+    elif lb is not None:
         window = np.exp(-np.pi * lb * t_pad) / np.sqrt(n_out)           # fid.py:136 with the ortho norm folded in
     delta = (t_pad[1] - t_pad[0]) if n_out > 1 else 1.0
     freqs = np.roll(np.fft.fftfreq(n_out, d=delta), n_out // 2)         # fourier.py:95, 31-32
@@ -81,11 +92,12 @@ def _win(geo, device):
         return None
     if geo["n_out"] not in D.SUPPORTED_N:
         return geo["window"]          # chirp-z path takes the float64 window as is
-    cache = geo.setdefault("_prepared", {})
-    key = (device.type, device.index)
-    if key not in cache:
-        cache[key] = D.PreparedWindow(geo["window"], geo["n_out"], device)
-    return cache[key]
+    with _GEO_LOCK:
+        cache = geo.setdefault("_prepared", {})
+        key = (device.type, device.index)
+        if key not in cache:
+            cache[key] = D.PreparedWindow(geo["window"], geo["n_out"], device)
+        return cache[key]
 
 
 def local_stats(fid_t, geo):
@@ -137,7 +149,7 @@ def apply_pass(fid_t, geo, p0, p1, pivot, out=None):
 
 
 def chain_single(fid_t, time_coord, target_points=None, position="end", lb=None, method="acme", peak_width=0.5,
-                 target_coord=None, p0_only=False, autophase_lb=0.0, out=None, exchange=None):
+                 target_coord=None, p0_only=False, autophase_lb=0.0, out=None, exchange=None, gb=None):
     """Full chain with the reference's ``mode="single"`` autophase on a ``[batch, n_in]`` device tensor.
 
     ``exchange`` (optional) is a callable ``(local_max, local_flat_index, search_fn) -> (p0, p1, pivot, fun)`` used by
@@ -146,7 +158,7 @@ def chain_single(fid_t, time_coord, target_points=None, position="end", lb=None,
     """
     n_in = fid_t.shape[-1]
     flat = fid_t.reshape(-1, n_in)
-    geo = chain_geometry(n_in, time_coord, target_points, position, lb)
+    geo = chain_geometry(n_in, time_coord, target_points, position, lb, gb)
     if exchange is None and autophase_lb == 0 and geo["n_out"] in D.SUPPORTED_N and flat.shape[0] > 0:
         return _chain_single_one_call(fid_t, flat, geo, method, peak_width, target_coord, p0_only, out)
     vmax, findex = local_stats(flat, geo)
@@ -180,16 +192,16 @@ def _chain_single_one_call(fid_t, flat, geo, method, peak_width, target_coord, p
                              pad_left=geo["pad_left"])
 
 
-def chain_to_spectrum(fid_t, time_coord, target_points=None, position="end", lb=None, out=None):
-    """``zero_fill -> apodize_exp -> to_spectrum`` only (one fused pass)."""
+def chain_to_spectrum(fid_t, time_coord, target_points=None, position="end", lb=None, out=None, gb=None):
+    """``zero_fill -> apodize_exp (or apodize_lg when ``gb`` is given) -> to_spectrum`` only (one fused pass)."""
     n_in = fid_t.shape[-1]
-    geo = chain_geometry(n_in, time_coord, target_points, position, lb)
+    geo = chain_geometry(n_in, time_coord, target_points, position, lb, gb)
     spec, _, _ = D.fid_to_spectrum(fid_t, n_out=geo["n_out"], pad_left=geo["pad_left"],
                                    window=_win(geo, fid_t.device), out=out)
     return spec, geo["freqs"], geo
 
 
-def run_chain_dataarray(da, dim, out_dim, target_points, position, lb, autophase_kwargs, baseline_kwargs=None):
+def run_chain_dataarray(da, dim, out_dim, target_points, position, lb, autophase_kwargs, baseline_kwargs=None, gb=None):
     """DataArray front end of the fused chain: same coords / attrs / lineage as the chained accessor calls.
 
     ``baseline_kwargs`` (``lam, p, n_iter``): additionally run ``baseline_als`` on the device-resident spectrum (the step
@@ -208,8 +220,12 @@ def run_chain_dataarray(da, dim, out_dim, target_points, position, lb, autophase
     if padded:
         attrs[ATTRS.zero_fill_target] = target_points
         attrs[ATTRS.zero_fill_position] = position
+    if gb is not None and lb is None:
+        lb = 1.0                                   # apodize_lg's default (fid.py:148)
     if lb is not None:
         attrs[ATTRS.apodization_lb] = lb
+        if gb is not None:
+            attrs[ATTRS.apodization_gb] = gb
         if name != dim:
             name = None
     target = out_dim if out_dim is not None else dim
@@ -222,11 +238,11 @@ def run_chain_dataarray(da, dim, out_dim, target_points, position, lb, autophase
 
         moved = np.ascontiguousarray(np.moveaxis(np.asarray(da.values), axis, -1), dtype=np.complex64)
         out_np, freqs, info = hostabi.chain_host(moved, t, target_points if padded else None, position, lb,
-                                                 autophase=autophase_kwargs)
+                                                 autophase=autophase_kwargs, gb=gb)
         spec = None
     elif autophase_kwargs is None:
         fid_t = P._to_device(da.values, axis)
-        spec, freqs, _ = chain_to_spectrum(fid_t, t, target_points if padded else None, position, lb)
+        spec, freqs, _ = chain_to_spectrum(fid_t, t, target_points if padded else None, position, lb, gb=gb)
         info = None
     else:
         fid_t = P._to_device(da.values, axis)
@@ -237,12 +253,12 @@ def run_chain_dataarray(da, dim, out_dim, target_points, position, lb, autophase
 
             spec, freqs, info = chain_all(fid_t, t, target_points if padded else None, position, lb,
                                           method=kw.get("method", "acme"), peak_width=kw.get("peak_width", 0.5),
-                                          target_coord=kw.get("target_coord"), p0_only=kw.get("p0_only", False))
+                                          target_coord=kw.get("target_coord"), p0_only=kw.get("p0_only", False), gb=gb)
         elif mode == "single":
             spec, freqs, info = chain_single(fid_t, t, target_points if padded else None, position, lb,
                                              method=kw.get("method", "acme"), peak_width=kw.get("peak_width", 0.5),
                                              target_coord=kw.get("target_coord"), p0_only=kw.get("p0_only", False),
-                                             autophase_lb=kw.get("lb", 0.0))
+                                             autophase_lb=kw.get("lb", 0.0), gb=gb)
         else:
             raise ValueError("Mode must be 'single' or 'all'.")
     dims = tuple(target if d == dim else d for d in da.dims)

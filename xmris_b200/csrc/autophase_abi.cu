@@ -33,6 +33,64 @@ __global__ void row_absmax_kernel(const float2* __restrict__ spec, long long bat
     }
 }
 
+// ---- the objective at given (p0, p1): one CTA per candidate, the 8 warps split the spectrum ---------------------------------
+// R = double: what the last search levels use; R = float: what the coarse levels use.  Partial sums combine in double.
+template <int METHOD, typename R>
+__global__ void __launch_bounds__(SEARCH_THREADS) score_kernel(const float2* __restrict__ spec, int n, double u0, double du,
+                                                               ScoreGeom geom, const double* __restrict__ p0,
+                                                               const double* __restrict__ p1, double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* sp = reinterpret_cast<float2*>(smem_raw);
+    __shared__ double part[SEARCH_THREADS / 32][4];
+    constexpr int NW = SEARCH_THREADS / 32;
+    const int per_warp = (n + NW - 1) / NW;
+    const int padshift = ilog2_ceil((per_warp + 31) / 32);
+    load_padded(sp, spec, n, padshift);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    R c0[1], s0[1];
+    RealOps<R>::sincospi2(R(p0[blockIdx.x] / 360.0), &s0[0], &c0[0]);
+    const int w0 = min(warp * per_warp, n), w1 = min(w0 + per_warp, n);
+    const int m0 = min(w0 + (lane << padshift), w1), m1 = min(m0 + (1 << padshift), w1);
+    Acc<R, METHOD, 1> acc;
+    acc.init();
+    lane_accumulate_rt<R, METHOD, 1>(sp, padshift, m0, m1, geom, R(p1[blockIdx.x] / 360.0), R(u0), R(du), c0, s0, acc);
+    acc.warp_reduce();
+    if (lane == 0)
+        for (int s = 0; s < 4; ++s) part[warp][s] = double(acc.a[0][s]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Acc<double, METHOD, 1> tot;
+        for (int s = 0; s < 4; ++s) {
+            double v = part[0][s];
+            for (int w = 1; w < NW; ++w) v = Acc<double, METHOD, 1>::comb(s, v, part[w][s]);
+            tot.a[0][s] = v;
+        }
+        out[blockIdx.x] = tot.template score<true>(0, geom);
+    }
+}
+
+template <int METHOD>
+int run_score(const float2* spec, int n, double u0, double du, ScoreGeom geom, const double* p0, const double* p1, int k,
+              int use_f64, double* out, cudaStream_t st) {
+    const int per_warp = (n + 7) / 8, Lz = (per_warp + 31) / 32;
+    int ps = 0;
+    while ((1 << ps) < Lz) ++ps;
+    const size_t smem = sizeof(float2) * (size_t(n) + (size_t(n) >> ps) + 2);
+    cudaError_t e;
+    if (use_f64) {
+        e = cudaFuncSetAttribute(score_kernel<METHOD, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "cudaFuncSetAttribute(score f64)");
+        score_kernel<METHOD, double><<<k, SEARCH_THREADS, smem, st>>>(spec, n, u0, du, geom, p0, p1, out);
+    } else {
+        e = cudaFuncSetAttribute(score_kernel<METHOD, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "cudaFuncSetAttribute(score f32)");
+        score_kernel<METHOD, float><<<k, SEARCH_THREADS, smem, st>>>(spec, n, u0, du, geom, p0, p1, out);
+    }
+    e = cudaGetLastError();
+    return e == cudaSuccess ? XMR_OK : xmr_abi::cuda_fail(e, "score launch");
+}
+
 constexpr int WS_LIST = 4096;   // candidates per ping-pong list
 
 // Search geometry (xmr_autophase_search_tuning): coarse grid steps in degrees, number of distinct coarse cells refined
@@ -43,6 +101,7 @@ struct SearchTuning {
     int f32_levels = 2;      // leading zoom levels evaluated in float32 (all `starts` basins)
     int late_starts = 2;     // basins kept for the float64 levels
     double first_ratio = 2.5;   // window shrink factor from zoom level 0 to level 1 (5 between all later levels)
+    int polish_starts = 3;      // ACME: basins finished by the float64 Newton polish after the float32 levels (0: float64 zoom levels)
 };
 SearchTuning g_tuning;
 
@@ -113,7 +172,10 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
     double h0 = sp.p0_step, h1 = p0_only ? 0.0 : sp.p1_step;
     zp.sep0 = 2.0 * sp.p0_step;
     zp.sep1 = p0_only ? 0.0 : 2.0 * sp.p1_step;
-    const int levels = g_tuning.levels;
+    // ACME: the float32 zoom levels localise the basins, the float64 Newton polish (search_polish_kernel) finishes them;
+    // the ROI methods (piecewise-constant minima) keep the float64 zoom levels
+    const bool polish = (METHOD == METHOD_ACME) && g_tuning.polish_starts > 0;
+    const int levels = polish ? (g_tuning.f32_levels < g_tuning.levels ? g_tuning.f32_levels : g_tuning.levels) : g_tuning.levels;
     int starts_prev = 0;
     double ratio_prev = 1.0;
     for (int lvl = 0; lvl < levels; ++lvl) {
@@ -150,7 +212,47 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
         h0 /= ratio_prev;
         h1 /= ratio_prev;
     }
-    const int n_starts = starts_prev;
+    int n_starts = starts_prev;
+    if (polish) {
+        PolishParams pp;
+        pp.spec = spec;
+        pp.n = n;
+        pp.u0 = u0;
+        pp.du = du;
+        pp.prev = prev;
+        pp.n_prev = (levels == 0) ? n_prev : n_prev * n_starts;    // no zoom level ran: the coarse grid's list
+        pp.sep0 = 2.0 * h0 * ratio_prev;       // further apart than the last level's window: another basin
+        pp.sep1 = p0_only ? 0.0 : 2.0 * h1 * ratio_prev;
+        pp.p1_lo = sp.p1_lo;
+        pp.p1_hi = sp.p1_hi;
+        pp.p0_only = p0_only;
+        pp.out = cur;
+        const int chunk = (n + SEARCH_THREADS - 1) / SEARCH_THREADS;
+        int psp = 0;
+        while ((1 << psp) < chunk) ++psp;
+        const size_t smem_polish = sizeof(float2) * (size_t(n) + (size_t(n) >> psp) + 2);
+        e = cudaFuncSetAttribute(search_polish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_polish));
+        if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "cudaFuncSetAttribute(search_polish)");
+        search_polish_kernel<<<g_tuning.polish_starts, SEARCH_THREADS, smem_polish, st>>>(pp);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_polish launch");
+        // one fine float64 zoom level around every polished point: where the entropy term dominates the objective is rough
+        // below ~0.3 deg (one kink per spectral point) and the lowest point of that neighbourhood is found by direct search
+        zp.first_level = 0;
+        zp.prev = cur;
+        zp.n_prev = 1;
+        zp.n_starts = g_tuning.polish_starts;
+        zp.h0 = 0.3;
+        zp.h1 = p0_only ? 0.0 : 0.9;
+        Cand* fin = (cur == listB) ? listA : listB;
+        zp.cur = fin;
+        search_zoom_kernel<METHOD, double, 4><<<zp.rows * (ZOOM_SPAN / 4) * zp.n_starts, SEARCH_THREADS, smem_zoom, st>>>(zp);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_zoom (final) launch");
+        prev = fin;
+        n_prev = zp.rows * ZOOM_SPAN;
+        n_starts = g_tuning.polish_starts;
+    }
     search_finalize_kernel<<<1, SEARCH_THREADS, 0, st>>>(prev, n_prev * n_starts, result);
     e = cudaGetLastError();
     if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_finalize launch");
@@ -190,7 +292,36 @@ int xmr_autophase_search_tuning(double p0_step_deg, double p1_step_deg, int star
     return XMR_OK;
 }
 
+int xmr_autophase_search_polish(int starts) {
+    if (starts < 0 || starts > ZOOM_MAX_STARTS) return xmr_abi::fail(XMR_ERR_BAD_ARG, "polish starts=%d must lie in [0, %d]", starts, ZOOM_MAX_STARTS);
+    g_tuning.polish_starts = starts;
+    return XMR_OK;
+}
+
 int64_t xmr_autophase_workspace_bytes(void) { return int64_t(sizeof(Cand)) * 2 * WS_LIST; }
+
+int xmr_autophase_score_c64(const void* spec_dev, int n, double u0, double du, int method, int target_idx, int index_width,
+                            const double* p0_dev, const double* p1_dev, int k, int use_f64, double* out_dev, void* stream) {
+    if (n < 2 || n > 8192) return xmr_abi::fail(XMR_ERR_UNSUPPORTED_N, "autophase score: n=%d must lie in [2, 8192]", n);
+    if (k < 0) return xmr_abi::fail(XMR_ERR_BAD_ARG, "k=%d", k);
+    if (k == 0) return XMR_OK;
+    if (!spec_dev || !p0_dev || !p1_dev || !out_dev) return xmr_abi::fail(XMR_ERR_BAD_ARG, "NULL pointer");
+    if (target_idx < 0 || target_idx >= n || index_width < 1)
+        return xmr_abi::fail(XMR_ERR_BAD_ARG, "bad target_idx=%d / index_width=%d", target_idx, index_width);
+    ScoreGeom g;
+    g.n = n;
+    g.target_idx = target_idx;
+    g.roi_start = target_idx - index_width > 0 ? target_idx - index_width : 0;
+    g.roi_end = target_idx + index_width < n ? target_idx + index_width : n;
+    const float2* s = static_cast<const float2*>(spec_dev);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (method) {
+        case XMR_METHOD_ACME: return run_score<METHOD_ACME>(s, n, u0, du, g, p0_dev, p1_dev, k, use_f64, out_dev, st);
+        case XMR_METHOD_PEAK_MINIMA: return run_score<METHOD_PEAK_MINIMA>(s, n, u0, du, g, p0_dev, p1_dev, k, use_f64, out_dev, st);
+        case XMR_METHOD_POSITIVITY: return run_score<METHOD_POSITIVITY>(s, n, u0, du, g, p0_dev, p1_dev, k, use_f64, out_dev, st);
+        default: return xmr_abi::fail(XMR_ERR_BAD_ARG, "method=%d", method);
+    }
+}
 
 int xmr_autophase_search_c64(const void* spec_dev, int n, double u0, double du, int method, int target_idx,
                              int index_width, int p0_only, double* result_dev, void* workspace_dev, void* stream) {

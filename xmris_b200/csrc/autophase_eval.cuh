@@ -86,6 +86,9 @@ struct Acc {
                 a[k][s] = v;
             }
     }
+    // RAW: the reference's formula as written, including the negative branch max(d) <= 0 that the searches reject
+    // (xmr_autophase_score_c64: the evaluator checked against the reference's own score functions).
+    template <bool RAW = false>
     __device__ __forceinline__ R score(int k, const ScoreGeom& g) const {
         if (METHOD == METHOD_ACME) {
             const R LN2 = R(0.69314718055994530942);
@@ -98,7 +101,7 @@ struct Acc {
             // objective is negative with a pole at max(d) -> 0- (SURVEY finding 5).  Such upside-down candidates are
             // rejected: the search minimises over the region max(d) > 0, which is where the reference's optimiser
             // lands on well-posed data.
-            if (!(a[k][3] > R(0))) return RealOps<R>::inf();
+            if (!RAW && !(a[k][3] > R(0))) return RealOps<R>::inf();
             return RealOps<R>::div(H + R(1000) * a[k][2], R(g.n) * a[k][3]);
         }
         if (METHOD == METHOD_POSITIVITY) return R(5) * a[k][0] - a[k][1];

@@ -5,6 +5,7 @@
 // same closed box by clamping.  SURVEY.md Appendix C / tests/test_autophase_gpu.py: this lands on the reference's
 // optimum to a few 1e-3 degrees.
 #pragma once
+#include "acme_grad.cuh"
 #include "autophase_eval.cuh"
 
 namespace xmr {
@@ -237,6 +238,186 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_zoom_kernel(const __gri
         c.pad = 0;
         p.cur[blockIdx.x * K + k] = c;
     }
+}
+
+// ---- ACME polish: bounded Newton on the analytic gradient, float64, one CTA per start ---------------------------------------
+// Replaces the two float64 zoom levels of round 1: from the best mutually distinct candidates of the last
+// float32 zoom level, iterate x <- x - H^-1 g with the analytic gradient (acme_grad.cuh) and a secant Hessian until the step
+// is below 1e-3 deg, then try the two neighbouring branches of the max(d) envelope ("kink hop").  Converges to the local
+// minimum to ~1e-4 deg in 4-6 iterations -- the point the reference's own optimiser converges to when it is run with a tight
+// tolerance (profiles/parity_r2.json).
+struct PolishParams {
+    const float2* spec;
+    int n;
+    double u0, du;
+    const Cand* prev;     // all candidates of the previous level (one list)
+    int n_prev;
+    double sep0, sep1;    // two candidates further apart than this are different basins
+    double p1_lo, p1_hi;
+    int p0_only;
+    Cand* out;            // one result per CTA
+};
+
+constexpr int POLISH_MAXIT = 10;
+
+struct PolishShared {
+    double part[SEARCH_THREADS / 32][3][GRAD_NSUMS];
+    double y0, y1;        // trial point of this round
+    int frozen;
+    int go;
+};
+
+// all threads: evaluate (f, g) at (y0, y1), (y0 + h0, y1), (y0, y1 + h1); thread 0 receives the three results
+__device__ __forceinline__ void polish_eval(const float2* sp, int padshift, int n, double u0, double du, int m0, int m1,
+                                            PolishShared& sh, FG (&out)[3], GradSums<double>* base_sums) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double y0 = sh.y0, y1 = sh.y1;
+    const int frozen = sh.frozen;
+    // per-point arithmetic in float32 (random 1e-7 relative errors average out over the sums; the anchor phase of every
+    // thread's short chunk is reduced in float64), cross-warp combination and everything after it in float64
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) {
+        GradSums<float> a;
+        a.init();
+        const double q0 = y0 + (k == 1 ? NEWTON_H0 : 0.0), q1 = y1 + (k == 2 ? NEWTON_H1 : 0.0);
+        // fold the first-order phase at the chunk start into the zero-order term in float64: lane_grad's own float32
+        // reduction then only sees |turns| < 1 plus the small in-chunk ramp
+        const double um0 = u0 + du * double(m0);
+        double t0 = q0 / 360.0 + (q1 / 360.0) * um0;
+        t0 -= floor(t0);
+        lane_grad<float>(sp, padshift, m0, m1, n, float(t0), float(q1 / 360.0), float(-du * double(m0)), float(du), frozen, a);
+        // (u restarts at 0 inside the chunk: shift the u-weighted sums back to the global ramp)
+        a.gP1 += float(um0) * a.gP0;
+        a.As1 += float(um0) * a.As0;
+        a.Al1 += float(um0) * a.Al0;
+        a.umax += float(um0);
+        a.warp_reduce();
+        if (lane == 0) grad_store(a, sh.part[warp][k]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 3; ++k) {
+            GradSums<double> tot = grad_load(sh.part[0][k]);
+            for (int w = 1; w < SEARCH_THREADS / 32; ++w) tot.merge(grad_load(sh.part[w][k]));
+            out[k] = acme_finish(tot, n);
+            if (k == 0 && base_sums) *base_sums = tot;
+        }
+    }
+    __syncthreads();
+}
+
+// CTA-wide Newton iteration from (x0, x1) in the given branch mode; returns the final point, its value and the sums there
+__device__ __forceinline__ void polish_run(const float2* sp, int padshift, int n, double u0, double du, int m0, int m1,
+                                           const PolishParams& p, PolishShared& sh, int frozen, int maxit, double& x0, double& x1,
+                                           double& fx, GradSums<double>& sums_x) {
+    NewtonState st;
+    st.x0 = x0; st.x1 = x1; st.f = CUDART_INF; st.g0 = st.g1 = 0.0; st.done = 0; st.iters = 0;
+    FG ax0, ax1;                 // offset gradients at the accepted point
+    double step0 = 0.0, step1 = 0.0;
+    int rejects = 0;
+    if (threadIdx.x == 0) { sh.y0 = x0; sh.y1 = x1; sh.frozen = frozen; sh.go = 1; }
+    __syncthreads();
+    for (int it = 0; it < maxit; ++it) {
+        FG r[3];
+        GradSums<double> bs;
+        polish_eval(sp, padshift, n, u0, du, m0, m1, sh, r, &bs);
+        if (threadIdx.x == 0) {
+            const bool first = (it == 0);
+            const bool small = fabs(step0) < 0.05 && fabs(step1) < 0.15;      // inside the quadratic bowl: trust the gradient
+            if (first || r[0].f < st.f || (small && r[0].f <= st.f * (1.0 + 1e-6))) {
+                st.x0 = sh.y0; st.x1 = sh.y1; st.f = r[0].f; st.g0 = r[0].g0; st.g1 = r[0].g1;
+                ax0 = r[1]; ax1 = r[2];
+                sums_x = bs;
+                rejects = 0;
+                double t0, t1;
+                newton_step(st, ax0, ax1, p.p0_only, p.p1_lo, p.p1_hi, &t0, &t1);
+                step0 = t0 - st.x0; step1 = t1 - st.x1;
+                if (!(st.f < CUDART_INF) || (!first && fabs(step0) < NEWTON_TOL0 && fabs(step1) < NEWTON_TOL1)) sh.go = 0;
+                sh.y0 = t0; sh.y1 = t1;
+            } else {
+                ++rejects;
+                step0 /= 3.0; step1 /= 3.0;
+                sh.y0 = st.x0 + step0; sh.y1 = st.x1 + step1;
+                if (rejects > 5) sh.go = 0;
+            }
+        }
+        __syncthreads();
+        if (!sh.go) break;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { x0 = st.x0; x1 = st.x1; fx = st.f; }
+}
+
+__global__ void __launch_bounds__(SEARCH_THREADS) search_polish_kernel(const __grid_constant__ PolishParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* sp = reinterpret_cast<float2*>(smem_raw);
+    __shared__ PolishShared sh;
+    const int n = p.n;
+    const int chunk = (n + SEARCH_THREADS - 1) / SEARCH_THREADS;
+    const int padshift = ilog2_ceil(chunk);
+    load_padded(sp, p.spec, n, padshift);
+    // the (blockIdx+1)-th best candidate that is distinct from all better ones (block_argmin's barriers also publish `sp`)
+    Cand chosen[ZOOM_MAX_STARTS];
+    Cand centre = block_argmin(p.prev, p.n_prev);
+    for (int s = 1; s <= int(blockIdx.x); ++s) {
+        chosen[s - 1] = centre;
+        centre = block_argmin(p.prev, p.n_prev, chosen, s, p.sep0, p.sep1);
+    }
+    Cand res;
+    res.f = CUDART_INF; res.p0 = centre.p0; res.p1 = centre.p1; res.pad = 0;
+    if (centre.f < CUDART_INF) {             // (uniform over the CTA)
+        const int m0 = min(int(threadIdx.x) * chunk, n), m1 = min(m0 + chunk, n);
+        double x0 = centre.p0, x1 = centre.p1, fx = CUDART_INF;
+        GradSums<double> sx;
+        polish_run(sp, padshift, n, p.u0, p.du, m0, m1, p, sh, -1, POLISH_MAXIT, x0, x1, fx, sx);
+        // kink hop: f = min_k A/(N d_k) over the points k that can hold max(d); try the two neighbours of the current one
+        __shared__ double bx0, bx1, bf;
+        __shared__ int kstar;
+        if (threadIdx.x == 0) {
+            bx0 = x0; bx1 = x1; bf = fx;
+            kstar = int(llrint((sx.umax - p.u0) / p.du));
+        }
+        __syncthreads();
+        if (bf < CUDART_INF) {
+            const int k0 = kstar;
+            bool improved = false;
+            for (int side = -1; side <= 1; side += 2) {
+                const int alt = k0 + side;
+                if (alt < 0 || alt >= n) continue;
+                double y0 = bx0, y1 = bx1, fy = CUDART_INF;
+                GradSums<double> sy;
+                __syncthreads();
+                polish_run(sp, padshift, n, p.u0, p.du, m0, m1, p, sh, alt, 4, y0, y1, fy, sy);
+                // the true objective (free maximum) at the branch minimum
+                if (threadIdx.x == 0) { sh.y0 = y0; sh.y1 = y1; sh.frozen = -1; }
+                __syncthreads();
+                FG r[3];
+                polish_eval(sp, padshift, n, p.u0, p.du, m0, m1, sh, r, nullptr);
+                __shared__ int better;
+                if (threadIdx.x == 0) {
+                    better = (r[0].f < bf) ? 1 : 0;
+                    if (better) { bx0 = y0; bx1 = y1; bf = r[0].f; }
+                }
+                __syncthreads();
+                improved = improved || (better != 0);
+            }
+            if (improved) {
+                double y0 = bx0, y1 = bx1, fy = CUDART_INF;
+                GradSums<double> sy;
+                polish_run(sp, padshift, n, p.u0, p.du, m0, m1, p, sh, -1, 4, y0, y1, fy, sy);
+                if (threadIdx.x == 0 && fy <= bf) { bx0 = y0; bx1 = y1; bf = fy; }
+                __syncthreads();
+            }
+        }
+        if (threadIdx.x == 0) {
+            double w = fmod(bx0 + 180.0, 360.0);
+            if (w < 0) w += 360.0;
+            res.f = bf; res.p0 = w - 180.0; res.p1 = bx1;
+            // never return something worse than the grid point the polish started from
+            if (!(res.f <= centre.f)) { res.f = centre.f; res.p0 = centre.p0; res.p1 = centre.p1; }
+        }
+    }
+    if (threadIdx.x == 0) p.out[blockIdx.x] = res;
 }
 
 // final pick: result = {p0, p1, f, 0}

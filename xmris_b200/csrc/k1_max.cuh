@@ -26,7 +26,10 @@ struct K1MaxSmem {
     using C = FftCfg<N>;
     static constexpr size_t SLOT = (C::SIZE_B > C::N ? C::SIZE_B : C::N);   // complex elements: holds A, then B
     static constexpr size_t RING = size_t(K1MAX_STAGES) * C::SPB * SLOT * sizeof(float2);
-    static constexpr size_t RED = size_t(2) * C::SPB * 32 * sizeof(float) + 64;   // level-0 sums x2 (iteration parity) + the CTA's snapshot of the running maximum
+    // level-0 sums x2 (iteration parity) + level-1 maxima (their OWN buffer: when every group is pruned at level 1 there is no
+    // trailing barrier, and a warp racing into the next iteration writes its level-0 sum while slower warps still read the
+    // level-1 values) + the CTA's snapshot of the running maximum
+    static constexpr size_t RED = size_t(3) * C::SPB * 32 * sizeof(float) + 64;
     static constexpr size_t BAR = 64;
     static constexpr size_t TW1 = size_t(15 * 16) * sizeof(float2);
     static constexpr size_t TOTAL = RING + RED + BAR + TW1;
@@ -47,7 +50,8 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, 2) k1_max_kernel(const __g
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2* ring = reinterpret_cast<float2*>(smem_raw);
     float* red = reinterpret_cast<float*>(smem_raw + SM::RING);
-    float* run_s = red + 2 * C::SPB * 32;   // [2]: thread 0's read of the running maximum, double buffered by iteration parity
+    float* red1 = red + 2 * C::SPB * 32;    // level-1 maxima
+    float* run_s = red + 3 * C::SPB * 32;   // [2]: thread 0's read of the running maximum, double buffered by iteration parity
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + SM::RING + SM::RED);
     float2* tw1_tab = reinterpret_cast<float2*>(smem_raw + SM::RING + SM::RED + SM::BAR);
 
@@ -156,14 +160,14 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, 2) k1_max_kernel(const __g
                 for (int off = 1; off < 16; off <<= 1) mq += __shfl_xor_sync(0xffffffffu, mq, off);   // sum over b
                 mq = fmaxf(mq, __shfl_xor_sync(0xffffffffu, mq, 16));                                  // max over k1
             }
-            if ((t & 31) == 0) red[g * 32 + (t >> 5)] = mq;
+            if ((t & 31) == 0) red1[g * 32 + (t >> 5)] = mq;
             __syncthreads();                   // every survivor holds its exchange-A inputs: the slot may be reused
             bool skip1_all = true, skip1_mine = true;
 #pragma unroll
             for (int gg = 0; gg < C::SPB; ++gg) {
-                float m = red[gg * 32];
+                float m = red1[gg * 32];
 #pragma unroll
-                for (int w = 1; w < WPG; ++w) m = fmaxf(m, red[gg * 32 + w]);
+                for (int w = 1; w < WPG; ++w) m = fmaxf(m, red1[gg * 32 + w]);
                 const bool sk = (16.0f * m * 1.0001f < run2);     // groups pruned at level 0 wrote 0 -> skipped here too
                 skip1_all = skip1_all && sk;
                 if (gg == g) skip1_mine = sk;

@@ -503,3 +503,30 @@ def autophase_search(spec1d, u0, du, method="acme", target_idx=0, index_width=1,
                                                 int(target_idx), int(index_width), int(bool(p0_only)), _ptr(result),
                                                 _ptr(ws), _stream_ptr(stream)))
     return result
+
+
+def autophase_score(spec1d, u0, du, p0, p1, method="acme", target_idx=0, index_width=1, float64=True, stream=None):
+    """The autophase objective at the candidates ``(p0[k], p1[k])`` (degrees) on one device-resident spectrum.
+
+    What the searches minimise, evaluated by the same device code (``xmr_autophase_score_c64``); the reference's
+    ``_acme_score`` / ``_peak_minima_score`` / ``_roi_positivity_score`` (``phasing.py:100-157``).  Returns a CUDA float64
+    tensor ``[k]``.
+    """
+    torch = _torch()
+    lib = _lib.load()
+    _require_cuda(spec1d, "spec1d")
+    if spec1d.dim() != 1:
+        raise ValueError("autophase_score works on one 1-D spectrum")
+    if method not in _lib.METHODS:
+        raise ValueError("Method must be 'acme', 'peak_minima', or 'positivity'")
+    dev = spec1d.device
+    p0_t = torch.as_tensor(np.atleast_1d(np.asarray(p0, dtype=np.float64))).to(dev)
+    p1_t = torch.as_tensor(np.atleast_1d(np.asarray(p1, dtype=np.float64))).to(dev)
+    if p0_t.shape != p1_t.shape:
+        raise ValueError("p0 and p1 must have the same length")
+    out = torch.empty(p0_t.shape[0], dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.xmr_autophase_score_c64(_ptr(spec1d.contiguous()), spec1d.shape[0], float(u0), float(du),
+                                               _lib.METHODS[method], int(target_idx), int(index_width), _ptr(p0_t), _ptr(p1_t),
+                                               int(p0_t.shape[0]), int(bool(float64)), _ptr(out), _stream_ptr(stream)))
+    return out

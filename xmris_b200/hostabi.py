@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib, chain
 
 
-def chain_host(fid, time_coord, target_points=None, position="end", lb=None, autophase=None, out=None, chunk=0):
+def chain_host(fid, time_coord, target_points=None, position="end", lb=None, autophase=None, out=None, chunk=0, gb=None):
     """``zero_fill -> apodize_exp -> to_spectrum [-> autophase]`` on a host array ``fid[..., n_in]`` (complex64).
 
     ``autophase``: ``None`` (stop after ``to_spectrum``) or a dict with the reference's keyword names
@@ -25,7 +25,7 @@ def chain_host(fid, time_coord, target_points=None, position="end", lb=None, aut
     n_in = fid.shape[-1]
     bshape = fid.shape[:-1]
     batch = int(np.prod(bshape)) if bshape else 1
-    geo = chain.chain_geometry(n_in, time_coord, target_points, position, lb)
+    geo = chain.chain_geometry(n_in, time_coord, target_points, position, lb, gb)
     n_out, freqs = geo["n_out"], geo["freqs"]
     if n_out not in chain.D.SUPPORTED_N:
         raise ValueError(f"xmris_b200: the host chain needs a power-of-two length in [16, 8192], got {n_out}")

@@ -63,13 +63,13 @@ def _search_geometry(coords, peak_width, target_coord):
 
 
 def chain_all_device(fid_t, time_coord, target_points=None, position="end", lb=None, out=None, geo=None,
-                     method="acme", peak_width=0.5, target_coord=None, p0_only=False, stream=None):
+                     method="acme", peak_width=0.5, target_coord=None, p0_only=False, stream=None, gb=None):
     """FID batch ``[batch, n_in]`` (device) -> phased spectra + per-voxel angles, all on the device, one kernel."""
     torch = D._torch()
     D._require_cuda(fid_t, "fid")
     n_in = fid_t.shape[-1]
     if geo is None:
-        geo = chain.chain_geometry(n_in, time_coord, target_points, position, lb)
+        geo = chain.chain_geometry(n_in, time_coord, target_points, position, lb, gb)
     n_out = geo["n_out"]
     flat = fid_t.reshape(-1, n_in)
     if out is None:
@@ -86,10 +86,10 @@ def chain_all_device(fid_t, time_coord, target_points=None, position="end", lb=N
 
 
 def chain_all(fid_t, time_coord, target_points=None, position="end", lb=None, method="acme", peak_width=0.5,
-              target_coord=None, p0_only=False):
+              target_coord=None, p0_only=False, gb=None):
     """Like :func:`chain_all_device` with host copies of the per-voxel results.  Returns ``(spec, freqs, info)``."""
     r = chain_all_device(fid_t, time_coord, target_points, position, lb, None, None, method, peak_width, target_coord,
-                         p0_only)
+                         p0_only, gb=gb)
     bshape = tuple(fid_t.shape[:-1])
     freqs = r["freqs"]
     piv_idx = r["pivot_index"].cpu().numpy().reshape(bshape)

@@ -621,15 +621,19 @@ def autophase(da, dim: str = DIMS.frequency, method: str = "acme", mode: str = "
 
 def process_fid(da, dim: str = DIMS.time, out_dim: str = DIMS.frequency, target_points: int | None = None,
                 position: str = "end", lb: float | None = None, autophase_kwargs: dict | None = None,
-                baseline_kwargs: dict | None = None):
+                baseline_kwargs: dict | None = None, gb: float | None = None):
     """``zero_fill -> apodize_exp -> to_spectrum [-> autophase] [-> baseline_als]`` in fused device passes.
 
     Equivalent (same values, coords and lineage attrs) to the chained accessor calls
     ``da.xmr.zero_fill(...).xmr.apodize_exp(...).xmr.to_spectrum(...).xmr.autophase(...)[.xmr.baseline_als(...)]`` with
     ``dim=out_dim`` for the phase and baseline steps; pass ``autophase_kwargs=None`` to stop after ``to_spectrum``,
     ``baseline_kwargs=dict(lam=..., p=..., n_iter=...)`` (or ``{}``) to also subtract the AsLS baseline of the real part
-    without the spectrum leaving the device.
+    without the spectrum leaving the device.  ``gb`` given: the window is ``apodize_lg(lb, gb)`` (Lorentz-to-Gauss,
+    ``fid.py:147-198``; ``lb`` then defaults to 1.0 as there) instead of ``apodize_exp(lb)`` -- it rides the fused kernel's
+    table-window path, so the un-apodized padded array never exists.  ``autophase_kwargs`` uses the reference FUNCTION's
+    defaults (``peak_width=0.5``, ``phasing.py:166``); the accessor's ``autophase`` default is 100 (``accessor.py:634``) --
+    pass ``peak_width`` explicitly when mirroring accessor calls with an ROI method.
     """
     from .chain import run_chain_dataarray
 
-    return run_chain_dataarray(da, dim, out_dim, target_points, position, lb, autophase_kwargs, baseline_kwargs)
+    return run_chain_dataarray(da, dim, out_dim, target_points, position, lb, autophase_kwargs, baseline_kwargs, gb)
