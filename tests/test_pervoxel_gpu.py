@@ -77,8 +77,10 @@ def test_chain_all_matches_per_spectrum_reference(name, family, nvox, n_in, zf, 
             print(f"{name} voxel {i}: gpu ({p0:.3f}, {p1:.3f}) f={f_gpu:.6g}  ref ({ref[i,0]:.3f}, {ref[i,1]:.3f}) f={ref[i,3]:.6g}")
     print(f"{name}: match {n_match}  equal-or-better objective {n_better}  worse {n_worse}  ill-posed {n_ill}  of {nvox}")
     well = nvox - n_ill
-    assert n_worse <= max(1, int(0.07 * well)), (n_match, n_better, n_worse)
-    assert n_match >= 0.4 * well
+    # small-batch smoke version of tests/test_angle_parity_gpu.py (1024 spectra per shape with the tight-DE adjudicator,
+    # floors 94-99 %): here "worse" is against the UN-adjudicated reference answer only
+    assert n_worse <= max(2, int(0.10 * well)), (n_match, n_better, n_worse)
+    assert n_match >= 0.6 * well
 
 
 def test_autophase_mode_all_accessor():

@@ -185,7 +185,8 @@ def tight_best_of(tight, name, n):
     if not runs:
         return None, 0
     runs = np.stack(runs)                       # (seeds, n, 4)
-    k = np.argmin(runs[:, :, 2], axis=0)
+    fvals = np.where(runs[:, :, 2] > 0, runs[:, :, 2], np.inf)      # a run that dived into the ACME pole (f < 0) is no adjudicator
+    k = np.argmin(fvals, axis=0)
     return runs[k, np.arange(runs.shape[1])], len(runs)
 
 

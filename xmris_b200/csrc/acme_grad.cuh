@@ -71,6 +71,7 @@ __device__ __forceinline__ GradSums<double> grad_load(const double* o) {
 
 struct FG {
     double f, g0, g1;   // objective and its gradient per degree of (p0, p1)
+    double H, pen;      // its two parts: entropy term and 1000 * penalty (f = (H + pen) / (N max d))
 };
 
 __device__ __forceinline__ FG acme_finish(const GradSums<double>& s, int n) {
@@ -79,6 +80,8 @@ __device__ __forceinline__ FG acme_finish(const GradSums<double>& s, int n) {
     if (!(s.dmax > 0.0) || !(s.G2 > 0.0)) {       // upside-down candidate (DESIGN.md deviation 7) or a constant spectrum
         r.f = CUDART_INF;
         r.g0 = r.g1 = 0.0;
+        r.H = 0.0;
+        r.pen = CUDART_INF;
         return r;
     }
     const double G = 0.5 * s.G2, T = 0.5 * LN2 * (s.T2 - s.G2);
@@ -91,6 +94,8 @@ __device__ __forceinline__ FG acme_finish(const GradSums<double>& s, int n) {
     const double Dm = s.dmax, dD0 = -s.qmax, dD1 = -s.qmax * s.umax;
     const double den = double(n) * Dm;
     r.f = A / den;
+    r.H = H;
+    r.pen = 1000.0 * s.P;
     r.g0 = RAD * (dA0 * Dm - A * dD0) / (den * Dm);
     r.g1 = RAD * (dA1 * Dm - A * dD1) / (den * Dm);
     return r;
@@ -100,7 +105,10 @@ __device__ __forceinline__ FG acme_finish(const GradSums<double>& s, int n) {
 // difference terms D_m for m in [m0, m1) (reads point m1 when m1 < n to close the last one).
 // turns0 = p0/360, tpu = p1/360 (turns per unit u), u_m = u0 + du*m.  FROZEN >= 0: (dmax, qmax, umax) are taken at that
 // point instead of at the maximum.
-template <typename R>
+// REANCHOR: the incremental phasor is recomputed exactly every REANCHOR points (0: only at the chunk start).  In float32 the
+// recurrence drifts by ~6e-8 per step in amplitude and phase; over a 64-point chunk that is a p1-dependent wobble of ~4e-6 in
+// the objective -- as much as 0.2 deg of p1 moves it along the flat valley (measured: profiles/parity_r2.json history).
+template <typename R, int REANCHOR = 0>
 __device__ __forceinline__ void lane_grad(const float2* sp, int padshift, int m0, int m1, int n, R turns0, R tpu, R u0, R du,
                                           int frozen, GradSums<R>& a) {
     if (m0 >= m1) return;
@@ -129,12 +137,20 @@ __device__ __forceinline__ void lane_grad(const float2* sp, int padshift, int m0
         if (frozen < 0 ? (dp > a.dmax) : (m0 == frozen)) { a.dmax = dp; a.qmax = qp; a.umax = u; }
     }
     const int mend = m1 < n ? m1 + 1 : m1;     // the point after the chunk only closes the last difference
+    const R ubase = u;
 #pragma unroll 2
     for (int m = m0 + 1; m < mend; ++m) {
-        const R ncr = cr * ci - sr * si;
-        sr = cr * si + sr * ci;
-        cr = ncr;
-        u += du;
+        if (REANCHOR > 0 && ((m - m0) % REANCHOR) == 0) {
+            u = ubase + du * R(m - m0);
+            R t = turns0 + tpu * u;
+            t -= floor(t);
+            O::sincospi2(t, &sr, &cr);
+        } else {
+            const R ncr = cr * ci - sr * si;
+            sr = cr * si + sr * ci;
+            cr = ncr;
+            u += du;
+        }
         const float2 S = sp[m + (m >> padshift)];
         const R d = R(S.x) * cr - R(S.y) * sr, q = R(S.x) * sr + R(S.y) * cr;
         const R uq = u * q;
@@ -173,7 +189,7 @@ struct NewtonState {
     int iters;
 };
 constexpr double NEWTON_H0 = 0.2, NEWTON_H1 = 0.8;        // secant offsets (degrees)
-constexpr double NEWTON_CAP0 = 8.0, NEWTON_CAP1 = 30.0;   // trust region of one step
+constexpr double NEWTON_CAP0 = 12.0, NEWTON_CAP1 = 40.0;  // trust region of one step
 constexpr double NEWTON_TOL0 = 1e-3, NEWTON_TOL1 = 3e-3;  // convergence: |step| below this
 
 // Proposes the next trial point from (f, g) at x and the gradients at the two offset points.  p0_only: x1 stays put.

@@ -102,6 +102,7 @@ struct SearchTuning {
     int late_starts = 2;     // basins kept for the float64 levels
     double first_ratio = 2.5;   // window shrink factor from zoom level 0 to level 1 (5 between all later levels)
     int polish_starts = 3;      // ACME: basins finished by the float64 Newton polish after the float32 levels (0: float64 zoom levels)
+    int polish_f32_levels = 1;  // ACME: float32 zoom levels before the polish (its trust region covers the second one)
 };
 SearchTuning g_tuning;
 
@@ -175,7 +176,7 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
     // ACME: the float32 zoom levels localise the basins, the float64 Newton polish (search_polish_kernel) finishes them;
     // the ROI methods (piecewise-constant minima) keep the float64 zoom levels
     const bool polish = (METHOD == METHOD_ACME) && g_tuning.polish_starts > 0;
-    const int levels = polish ? (g_tuning.f32_levels < g_tuning.levels ? g_tuning.f32_levels : g_tuning.levels) : g_tuning.levels;
+    const int levels = polish ? g_tuning.polish_f32_levels : g_tuning.levels;
     int starts_prev = 0;
     double ratio_prev = 1.0;
     for (int lvl = 0; lvl < levels; ++lvl) {
@@ -236,8 +237,11 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
         search_polish_kernel<<<g_tuning.polish_starts, SEARCH_THREADS, smem_polish, st>>>(pp);
         e = cudaGetLastError();
         if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_polish launch");
-        // one fine float64 zoom level around every polished point: where the entropy term dominates the objective is rough
-        // below ~0.3 deg (one kink per spectral point) and the lowest point of that neighbourhood is found by direct search
+        // Two fine float64 zoom levels finish the job by direct search.  Where the penalty term vanishes at the optimum (clean,
+        // all-positive spectra; data of amplitude ~1e9 like the reference's Bruker fixture) the minimum sits against the wall
+        // 1000 P > 0 of the feasible region -- a constrained optimum where the gradient does not vanish -- and where the
+        // entropy term dominates the objective is rough below ~0.3 deg (one kink per spectral point).
+        //   A: +-0.3 x +-0.9 deg (spacing 0.03 x 0.09) around every polished point;  B: +-0.06 x +-0.18 deg around the best
         zp.first_level = 0;
         zp.prev = cur;
         zp.n_prev = 1;
@@ -248,10 +252,21 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
         zp.cur = fin;
         search_zoom_kernel<METHOD, double, 4><<<zp.rows * (ZOOM_SPAN / 4) * zp.n_starts, SEARCH_THREADS, smem_zoom, st>>>(zp);
         e = cudaGetLastError();
-        if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_zoom (final) launch");
-        prev = fin;
+        if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_zoom (fine A) launch");
+        zp.first_level = 1;                               // the single best candidate over all starts of level A
+        zp.prev = fin;
+        zp.n_prev = zp.rows * ZOOM_SPAN * g_tuning.polish_starts;
+        zp.n_starts = 1;
+        zp.h0 = 0.06;
+        zp.h1 = p0_only ? 0.0 : 0.18;
+        zp.cur = cur;
+        search_zoom_kernel<METHOD, double, 4><<<zp.rows * (ZOOM_SPAN / 4), SEARCH_THREADS, smem_zoom, st>>>(zp);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_zoom (fine B) launch");
+        // the final pick sees level B (which contains A's best point: its window centre)
+        prev = cur;
         n_prev = zp.rows * ZOOM_SPAN;
-        n_starts = g_tuning.polish_starts;
+        n_starts = 1;
     }
     search_finalize_kernel<<<1, SEARCH_THREADS, 0, st>>>(prev, n_prev * n_starts, result);
     e = cudaGetLastError();

@@ -329,6 +329,10 @@ __device__ __forceinline__ void polish_run(const float2* sp, int padshift, int n
                 ax0 = r[1]; ax1 = r[2];
                 sums_x = bs;
                 rejects = 0;
+                // an offset point beyond the wall of the feasible region (its value explodes) says nothing about curvature
+                // on this side: creep towards the wall along the gradient instead (rejections shrink the step)
+                if (!(ax0.f < 4.0 * st.f)) { ax0 = r[0]; ax0.g0 = st.g0 + (st.g0 < 0.0 ? -1.0 : 1.0) * fabs(st.g0) * NEWTON_H0 / 0.05; }
+                if (!(ax1.f < 4.0 * st.f)) { ax1 = r[0]; ax1.g1 = st.g1 + (st.g1 < 0.0 ? -1.0 : 1.0) * fabs(st.g1) * NEWTON_H1 / 0.15; }
                 double t0, t1;
                 newton_step(st, ax0, ax1, p.p0_only, p.p1_lo, p.p1_hi, &t0, &t1);
                 step0 = t0 - st.x0; step1 = t1 - st.x1;

@@ -1,5 +1,6 @@
 // One instantiation set of K2 (per-voxel chain) per transform length: compile with -DXMR_N=<N>.
 #include "k2_launch.cuh"
+#include "k2_acme.cuh"
 
 #ifndef XMR_N
 #error "compile with -DXMR_N=<transform length>"
@@ -7,11 +8,20 @@
 
 namespace xmr {
 
+template <int N, int METHOD> struct K2Pick {          // ROI methods: the round-1 grid + zoom kernel
+    static constexpr auto kern = k2_kernel<N, METHOD>;
+    static constexpr size_t smem = K2Smem<N>::TOTAL;
+};
+template <int N> struct K2Pick<N, METHOD_ACME> {       // ACME: series localisation + quasi-Newton on the analytic gradient
+    static constexpr auto kern = k2_acme_kernel<N>;
+    static constexpr size_t smem = K2aSmem<N>::TOTAL;
+};
+
 template <int N, int METHOD>
 static cudaError_t launch_k2(const K2Params& p, cudaStream_t st) {
     using C = FftCfg<N>;
-    auto kern = k2_kernel<N, METHOD>;
-    constexpr size_t smem = K2Smem<N>::TOTAL;
+    auto kern = K2Pick<N, METHOD>::kern;
+    constexpr size_t smem = K2Pick<N, METHOD>::smem;
     static thread_local int cached_dev = -1;
     static thread_local int ctas_per_wave = 0;
     int dev = 0;
