@@ -191,8 +191,12 @@ int xmr_host_workspace_release(void);
  * (window_mode / window_dev / win_rows_host).
  *   workspace_dev  at least xmr_chain_single_workspace_bytes(batch, n_out) bytes of device memory, caller-owned
  *   result_host    double[6] = {p0 deg, p1 deg, pivot index on the output axis, objective, global max |S|, winning row}
- * Synchronises `stream` three times (16 + 4 + 32 bytes read back); pass 2 is enqueued when it returns. */
+ * No host read-back between the passes: the winning row, its pivot and the phase parameters of pass 2 stay in device memory
+ * (workspace control block); the call returns -- with pass 2 enqueued on `stream` -- once the 256-byte control block has
+ * arrived on a side stream. */
 int64_t xmr_chain_single_workspace_bytes(int64_t batch, int n_out);
+/* diagnostic: how many calls of xmr_chain_single_dev_c64 replayed their captured CUDA graph (process-wide) */
+int64_t xmr_chain_single_graph_launches(void);
 int xmr_chain_single_dev_c64(const xmr_host_chain_desc* desc, const void* fid_dev, void* spec_dev, int64_t batch,
                              int window_mode, const float* window_dev, const float* win_rows_host, void* workspace_dev,
                              double* result_host, void* stream);

@@ -231,3 +231,31 @@ def test_baseline_als_middle_axis_and_real_input():
     g = load_golden("baseline")
     corrected, _ = orc.baseline_als(g["real_in"], 1, lam=1e6, p=0.001, n_iter=10)
     assert np.array_equal(corrected, g["real_corr"])
+
+
+def test_angle_parity_fixture_is_the_reference_optimiser():
+    """tests/golden/angle_parity_ref.npz holds the reference's DE answers on the seeded problem set (tools/angle_parity.py):
+    re-run the oracle on a few spectra and compare bit-exactly; the tight-DE adjudicator is never worse than the reference
+    on these and lies in the box."""
+    import os
+    import sys
+
+    from conftest import ROOT
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import angle_parity as ap
+
+    shape = [s for s in ap.SHAPES if s[0] == "C4_13C_1024"][0]
+    _, _, spec, freqs = ap.spectra(shape, 3)
+    ref = np.load(os.path.join(ap.GOLD, "angle_parity_ref.npz"))[shape[0]]
+    tight = np.load(os.path.join(ap.GOLD, "angle_parity_tight.npz"))
+    assert ref.shape == (ap.N_SET, 6)
+    for i in range(3):
+        _, info = orc.autophase(spec[i], 0, freqs, peak_width=100)
+        assert (info["p0"], info["p1"], info["pivot"], info["fun"]) == tuple(ref[i, :4])
+    for sh in ap.SHAPES:
+        tb, nseeds = ap.tight_best_of(tight, sh[0], ap.N_SET)
+        assert nseeds == len(ap.TIGHT_SEEDS) and tb.shape == (ap.N_SET, 4)
+        assert np.all(tb[:, 2] > 0) and np.all(np.abs(tb[:, 0]) <= 180.0) and np.all(np.abs(tb[:, 1]) <= 4000.0)
+        r = np.load(os.path.join(ap.GOLD, "angle_parity_ref.npz"))[sh[0]]
+        assert np.mean(tb[:, 2] <= r[:, 3] * (1 + 1e-6)) > 0.97      # the tight run is (almost) never worse than the reference

@@ -175,3 +175,26 @@ def test_host_c_abi_chain_matches_device_chain(mode, n_in, zf):
     np.testing.assert_array_equal(freqs, rfreqs)
     assert np.array_equal(out.reshape(batch, -1), ref.cpu().numpy())
     hostabi.release_workspace()
+
+
+def test_device_chain_replays_a_cuda_graph_and_gives_the_same_result():
+    import torch
+
+    """xmr_chain_single_dev_c64 captures its launches up to the search's final kernel once per argument set (second call) and
+    replays the graph afterwards: same angles and spectra as the eager first call, and the replay counter moves."""
+    from xmris_b200 import _lib, chain
+    from xmris_b200.synth import make_fids_torch
+
+    lib = _lib.load()
+    fid, t = make_fids_torch("1H", 3000, 1024, torch.device("cuda:0"), seed=77)
+    outs, infos = [], []
+    before = lib.xmr_chain_single_graph_launches()
+    for _ in range(4):
+        out, _, info = chain.chain_single(fid, t, 2048, "end", 5.0, peak_width=100)
+        outs.append(out.clone())
+        infos.append(info)
+    torch.cuda.synchronize()
+    assert lib.xmr_chain_single_graph_launches() - before >= 2          # calls 2..4 run the captured graph
+    for o, i in zip(outs[1:], infos[1:]):
+        assert i["p0"] == infos[0]["p0"] and i["p1"] == infos[0]["p1"] and i["pivot"] == infos[0]["pivot"]
+        assert torch.equal(o, outs[0])

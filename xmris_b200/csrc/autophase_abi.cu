@@ -91,7 +91,7 @@ int run_score(const float2* spec, int n, double u0, double du, ScoreGeom geom, c
     return e == cudaSuccess ? XMR_OK : xmr_abi::cuda_fail(e, "score launch");
 }
 
-constexpr int WS_LIST = 4096;   // candidates per ping-pong list
+constexpr int WS_LIST = 8192;   // candidates per ping-pong list
 
 // Search geometry (xmr_autophase_search_tuning): coarse grid steps in degrees, number of distinct coarse cells refined
 // side by side, nested zoom levels (each shrinks the window by 5).
@@ -102,13 +102,21 @@ struct SearchTuning {
     int late_starts = 2;     // basins kept for the float64 levels
     double first_ratio = 2.5;   // window shrink factor from zoom level 0 to level 1 (5 between all later levels)
     int polish_starts = 3;      // ACME: basins finished by the float64 Newton polish after the float32 levels (0: float64 zoom levels)
+    int fine_b = 1;             // ACME: second fine float64 level (+-0.06 x +-0.18 deg, spacing 0.006 x 0.018) after level A
     int polish_f32_levels = 1;  // ACME: float32 zoom levels before the polish (its trust region covers the second one)
 };
 SearchTuning g_tuning;
 
+// pivot_dev (optional): the pivot index lives in device memory (u0 = -du*idx, ROI around idx): the geometry is resolved on the
+// device (search_geom_kernel) and `u0` / `geom.target_idx` of the arguments are ignored.  ph_out (optional): K1PhaseDev for pass 2.
 template <int METHOD>
 int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, int p0_only, double* result, Cand* ws,
-               cudaStream_t st) {
+               cudaStream_t st, const int* pivot_dev = nullptr, int index_width = 1, void* ph_out = nullptr) {
+    SearchGeomDev* gd = nullptr;
+    if (pivot_dev != nullptr) {
+        gd = reinterpret_cast<SearchGeomDev*>(ws + 2 * WS_LIST);
+        search_geom_kernel<<<1, 32, 0, st>>>(pivot_dev, du, n, index_width, gd);
+    }
     const int Lc = (n + 31) / 32;
     int psc = 0;
     while ((1 << psc) < Lc) ++psc;
@@ -134,6 +142,7 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
     sp.u0 = u0;
     sp.du = du;
     sp.geom = geom;
+    sp.gd = gd;
     sp.p0_lo = -180.0;
     sp.p0_hi = 180.0;
     sp.p1_lo = p0_only ? 0.0 : -4000.0;
@@ -162,6 +171,8 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
     zp.u0 = u0;
     zp.du = du;
     zp.geom = geom;
+    zp.gd = gd;
+    zp.only_flagged = 0;
     zp.p0_lo = sp.p0_lo;
     zp.p0_hi = sp.p0_hi;
     zp.p1_lo = sp.p1_lo;
@@ -219,6 +230,7 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
         pp.spec = spec;
         pp.n = n;
         pp.u0 = u0;
+        pp.gd = gd;
         pp.du = du;
         pp.prev = prev;
         pp.n_prev = (levels == 0) ? n_prev : n_prev * n_starts;    // no zoom level ran: the coarse grid's list
@@ -234,7 +246,7 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
         const size_t smem_polish = sizeof(float2) * (size_t(n) + (size_t(n) >> psp) + 2);
         e = cudaFuncSetAttribute(search_polish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_polish));
         if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "cudaFuncSetAttribute(search_polish)");
-        search_polish_kernel<<<g_tuning.polish_starts, SEARCH_THREADS, smem_polish, st>>>(pp);
+        search_polish_kernel<<<g_tuning.polish_starts * POLISH_ROLES, SEARCH_THREADS, smem_polish, st>>>(pp);
         e = cudaGetLastError();
         if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_polish launch");
         // Two fine float64 zoom levels finish the job by direct search.  Where the penalty term vanishes at the optimum (clean,
@@ -245,7 +257,8 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
         zp.first_level = 0;
         zp.prev = cur;
         zp.n_prev = 1;
-        zp.n_starts = g_tuning.polish_starts;
+        zp.n_starts = g_tuning.polish_starts * POLISH_ROLES;      // (every role's result is a start of level A)
+        zp.only_flagged = 1;                                       // smooth optima: the polished point stands
         zp.h0 = 0.3;
         zp.h1 = p0_only ? 0.0 : 0.9;
         Cand* fin = (cur == listB) ? listA : listB;
@@ -253,22 +266,36 @@ int run_search(const float2* spec, int n, double u0, double du, ScoreGeom geom, 
         search_zoom_kernel<METHOD, double, 4><<<zp.rows * (ZOOM_SPAN / 4) * zp.n_starts, SEARCH_THREADS, smem_zoom, st>>>(zp);
         e = cudaGetLastError();
         if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_zoom (fine A) launch");
-        zp.first_level = 1;                               // the single best candidate over all starts of level A
-        zp.prev = fin;
-        zp.n_prev = zp.rows * ZOOM_SPAN * g_tuning.polish_starts;
-        zp.n_starts = 1;
-        zp.h0 = 0.06;
-        zp.h1 = p0_only ? 0.0 : 0.18;
-        zp.cur = cur;
-        search_zoom_kernel<METHOD, double, 4><<<zp.rows * (ZOOM_SPAN / 4), SEARCH_THREADS, smem_zoom, st>>>(zp);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_zoom (fine B) launch");
-        // the final pick sees level B (which contains A's best point: its window centre)
-        prev = cur;
-        n_prev = zp.rows * ZOOM_SPAN;
-        n_starts = 1;
+        if (g_tuning.fine_b) {
+            zp.first_level = 1;                           // the single best candidate over all starts of level A
+            zp.prev = fin;
+            zp.n_prev = zp.rows * ZOOM_SPAN * g_tuning.polish_starts * POLISH_ROLES;
+            zp.n_starts = 1;
+            zp.h0 = 0.06;
+            zp.h1 = p0_only ? 0.0 : 0.18;
+            zp.cur = cur;
+            zp.only_flagged = 1;                          // level B only where the optimum sits against the wall
+            search_zoom_kernel<METHOD, double, 4><<<zp.rows * (ZOOM_SPAN / 4), SEARCH_THREADS, smem_zoom, st>>>(zp);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_zoom (fine B) launch");
+            // the final pick sees level B (which contains A's best point: its window centre)
+            prev = cur;
+            n_prev = zp.rows * ZOOM_SPAN;
+            n_starts = 1;
+        } else {
+            prev = fin;
+            n_prev = zp.rows * ZOOM_SPAN;
+            n_starts = g_tuning.polish_starts * POLISH_ROLES;
+        }
     }
-    search_finalize_kernel<<<1, SEARCH_THREADS, 0, st>>>(prev, n_prev * n_starts, result);
+    FinalizePhase fp;
+    fp.ph_out = ph_out;
+    fp.gd = gd;
+    fp.u0 = u0;
+    fp.du = du;
+    fp.n = n;
+    fp.p0_only = p0_only;
+    search_finalize_kernel<<<1, SEARCH_THREADS, 0, st>>>(prev, n_prev * n_starts, result, fp);
     e = cudaGetLastError();
     if (e != cudaSuccess) return xmr_abi::cuda_fail(e, "search_finalize launch");
     return XMR_OK;
@@ -308,12 +335,12 @@ int xmr_autophase_search_tuning(double p0_step_deg, double p1_step_deg, int star
 }
 
 int xmr_autophase_search_polish(int starts) {
-    if (starts < 0 || starts > ZOOM_MAX_STARTS) return xmr_abi::fail(XMR_ERR_BAD_ARG, "polish starts=%d must lie in [0, %d]", starts, ZOOM_MAX_STARTS);
+    if (starts < 0 || starts * POLISH_ROLES > ZOOM_MAX_STARTS + 1) return xmr_abi::fail(XMR_ERR_BAD_ARG, "polish starts=%d must lie in [0, %d]", starts, (ZOOM_MAX_STARTS + 1) / POLISH_ROLES);
     g_tuning.polish_starts = starts;
     return XMR_OK;
 }
 
-int64_t xmr_autophase_workspace_bytes(void) { return int64_t(sizeof(Cand)) * 2 * WS_LIST; }
+int64_t xmr_autophase_workspace_bytes(void) { return int64_t(sizeof(Cand)) * 2 * WS_LIST + 256; }
 
 int xmr_autophase_score_c64(const void* spec_dev, int n, double u0, double du, int method, int target_idx, int index_width,
                             const double* p0_dev, const double* p1_dev, int k, int use_f64, double* out_dev, void* stream) {
@@ -337,6 +364,34 @@ int xmr_autophase_score_c64(const void* spec_dev, int n, double u0, double du, i
         default: return xmr_abi::fail(XMR_ERR_BAD_ARG, "method=%d", method);
     }
 }
+
+}  // extern "C"
+
+namespace xmr_abi {
+// the search with its geometry resolved on the device (pivot index in device memory) and the phase parameters of pass 2
+// written to device memory: the mode="single" chain without host read-backs (host_chain.cu)
+int autophase_search_dev(const void* spec_dev, int n, double du, int method, const int* pivot_dev, int fixed_pivot, double u0_fixed,
+                         int fixed_target, int index_width, int p0_only, double* result_dev, void* workspace_dev, void* ph_out,
+                         void* stream) {
+    ScoreGeom g;
+    g.n = n;
+    g.target_idx = fixed_pivot ? fixed_target : 0;
+    g.roi_start = g.target_idx - index_width > 0 ? g.target_idx - index_width : 0;
+    g.roi_end = g.target_idx + index_width < n ? g.target_idx + index_width : n;
+    const float2* s = static_cast<const float2*>(spec_dev);
+    Cand* ws = static_cast<Cand*>(workspace_dev);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int* piv = fixed_pivot ? nullptr : pivot_dev;
+    switch (method) {
+        case XMR_METHOD_ACME: return run_search<METHOD_ACME>(s, n, u0_fixed, du, g, p0_only, result_dev, ws, st, piv, index_width, ph_out);
+        case XMR_METHOD_PEAK_MINIMA: return run_search<METHOD_PEAK_MINIMA>(s, n, u0_fixed, du, g, p0_only, result_dev, ws, st, piv, index_width, ph_out);
+        case XMR_METHOD_POSITIVITY: return run_search<METHOD_POSITIVITY>(s, n, u0_fixed, du, g, p0_only, result_dev, ws, st, piv, index_width, ph_out);
+        default: return fail(XMR_ERR_BAD_ARG, "method=%d", method);
+    }
+}
+}  // namespace xmr_abi
+
+extern "C" {
 
 int xmr_autophase_search_c64(const void* spec_dev, int n, double u0, double du, int method, int target_idx,
                              int index_width, int p0_only, double* result_dev, void* workspace_dev, void* stream) {

@@ -14,11 +14,36 @@ struct Cand {
     double f, p0, p1, pad;
 };
 
+// Search geometry in DEVICE memory (the pivot is the winning spectrum's own |S| argmax, known only on the device when the
+// chain runs without host read-backs): written by search_geom_kernel, read by every search kernel when `gd` is set.
+struct SearchGeomDev {
+    double u0;
+    int target_idx, roi_start, roi_end;
+};
+__global__ void search_geom_kernel(const int* pivot_idx, double du, int n, int index_width, SearchGeomDev* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const int idx = *pivot_idx;
+        out->u0 = -du * double(idx);
+        out->target_idx = idx;
+        out->roi_start = idx - index_width > 0 ? idx - index_width : 0;
+        out->roi_end = idx + index_width < n ? idx + index_width : n;
+    }
+}
+__device__ __forceinline__ void resolve_geom(const SearchGeomDev* gd, double& u0, ScoreGeom& g) {
+    if (gd != nullptr) {
+        u0 = gd->u0;
+        g.target_idx = gd->target_idx;
+        g.roi_start = gd->roi_start;
+        g.roi_end = gd->roi_end;
+    }
+}
+
 struct SearchParams {
     const float2* spec;   // one spectrum, n points (global memory)
     int n;
     double u0, du;        // u_m = u0 + du*m = (x_m - pivot)/(x_max - x_min)
     ScoreGeom geom;
+    const SearchGeomDev* gd;   // optional: u0 / ROI from device memory
     double p0_lo, p0_hi, p0_step;
     int n_p0;
     double p1_lo, p1_hi, p1_step;
@@ -54,6 +79,9 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_coarse_kernel(const __g
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double u0g = p.u0;
+    ScoreGeom geom = p.geom;
+    resolve_geom(p.gd, u0g, geom);
     const int nchunks = (p.n_p0 + SEARCH_K - 1) / SEARCH_K;
     const long long items = (long long)p.n_p1 * nchunks;
     const int m0 = min(lane << padshift, n), m1 = min((lane + 1) << padshift, n);
@@ -72,12 +100,12 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_coarse_kernel(const __g
         }
         Acc<float, METHOD, SEARCH_K> acc;
         acc.init();
-        lane_accumulate_rt<float, METHOD, SEARCH_K>(sp, padshift, m0, m1, p.geom, float(p1 / 360.0), float(p.u0),
+        lane_accumulate_rt<float, METHOD, SEARCH_K>(sp, padshift, m0, m1, geom, float(p1 / 360.0), float(u0g),
                                                     float(p.du), c0, s0, acc);
         acc.warp_reduce();
 #pragma unroll
         for (int k = 0; k < SEARCH_K; ++k) {
-            const float f = acc.score(k, p.geom);
+            const float f = acc.score(k, geom);
             if (double(f) < best_f) { best_f = double(f); best_p0 = p0k[k]; best_p1 = p1; }
         }
     }
@@ -105,6 +133,9 @@ struct ZoomParams {
                         //    DISTINCT one): the coarse grid's list, or all blocks of a level that ran more starts;
                         // 0: prev holds one block of n_prev candidates per start
     double sep0, sep1;  // first level: two cells are distinct when they differ by more than this in p0 or in p1
+    const SearchGeomDev* gd;   // optional: u0 / ROI from device memory
+    int only_flagged;   // 1: evaluate the window only if the centre carries the wall flag (Cand::pad != 0); otherwise the
+                        //    centre itself is the only candidate reported
 };
 
 constexpr int ZOOM_MAX_STARTS = 8;  // the best distinct coarse cells are refined side by side (63 CTAs each)
@@ -187,9 +218,20 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_zoom_kernel(const __gri
         centre = block_argmin(p.prev + (size_t)start * p.n_prev, p.n_prev);
     }
     const bool dead = !(centre.f < CUDART_INF);           // no second basin: this start reports +inf
+    if (p.only_flagged && centre.pad == 0.0) {            // (CTA-uniform) smooth optimum: the polished point stands
+        if (threadIdx.x < K) {
+            Cand c = centre;
+            if (!(local == 0 && threadIdx.x == 0)) c.f = CUDART_INF;
+            p.cur[blockIdx.x * K + threadIdx.x] = c;
+        }
+        return;
+    }
 
     const int row = local / (ZOOM_SPAN / K), ch = local % (ZOOM_SPAN / K);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double u0g = p.u0;
+    ScoreGeom geom = p.geom;
+    resolve_geom(p.gd, u0g, geom);
     const double p1 = (p.rows == 1) ? centre.p1
                                     : fmin(fmax(centre.p1 + (row - ZOOM_SIDE / 2) * (p.h1 / (ZOOM_SIDE / 2)), p.p1_lo), p.p1_hi);
     R c0[K], s0[K];
@@ -207,7 +249,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_zoom_kernel(const __gri
     const int m0 = min(w0 + (lane << padshift), w1), m1 = min(m0 + (1 << padshift), w1);
     Acc<R, METHOD, K> acc;
     acc.init();
-    lane_accumulate_rt<R, METHOD, K>(sp, padshift, m0, m1, p.geom, R(p1 / 360.0), R(p.u0), R(p.du), c0, s0, acc);
+    lane_accumulate_rt<R, METHOD, K>(sp, padshift, m0, m1, geom, R(p1 / 360.0), R(u0g), R(p.du), c0, s0, acc);
     acc.warp_reduce();
     if (lane == 0) {
 #pragma unroll
@@ -226,7 +268,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_zoom_kernel(const __gri
             tot.a[0][s] = v;
         }
         Cand c;
-        c.f = tot.score(0, p.geom);
+        c.f = tot.score(0, geom);
         if (!(c.f == c.f) || dead) c.f = CUDART_INF;   // NaN never wins
         // select p0k[k] without dynamic register indexing
         double myp0 = p0k[0];
@@ -235,7 +277,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_zoom_kernel(const __gri
             if (kk == k) myp0 = p0k[kk];
         c.p0 = myp0;
         c.p1 = p1;
-        c.pad = 0;
+        c.pad = centre.pad;
         p.cur[blockIdx.x * K + k] = c;
     }
 }
@@ -256,13 +298,15 @@ struct PolishParams {
     double p1_lo, p1_hi;
     int p0_only;
     Cand* out;            // one result per CTA
+    const SearchGeomDev* gd;   // optional: u0 from device memory
 };
 
-constexpr int POLISH_MAXIT = 10;
+constexpr int POLISH_MAXIT = 8;
 
 struct PolishShared {
     double part[SEARCH_THREADS / 32][3][GRAD_NSUMS];
     double y0, y1;        // trial point of this round
+    double H, pen;        // entropy term and 1000 * penalty at the last accepted point
     int frozen;
     int go;
 };
@@ -326,6 +370,7 @@ __device__ __forceinline__ void polish_run(const float2* sp, int padshift, int n
             const bool small = fabs(step0) < 0.05 && fabs(step1) < 0.15;      // inside the quadratic bowl: trust the gradient
             if (first || r[0].f < st.f || (small && r[0].f <= st.f * (1.0 + 1e-6))) {
                 st.x0 = sh.y0; st.x1 = sh.y1; st.f = r[0].f; st.g0 = r[0].g0; st.g1 = r[0].g1;
+                sh.H = r[0].H; sh.pen = r[0].pen;
                 ax0 = r[1]; ax1 = r[2];
                 sums_x = bs;
                 rejects = 0;
@@ -352,86 +397,126 @@ __device__ __forceinline__ void polish_run(const float2* sp, int padshift, int n
     if (threadIdx.x == 0) { x0 = st.x0; x1 = st.x1; fx = st.f; }
 }
 
+// grid = starts x POLISH_ROLES.  Role 0 minimises the objective itself; roles 1, 2 minimise the smooth branch functions
+// f_k = A / (N d_k) of the two neighbours k = kmax -+ 1 of the |S| maximum (f = min_k f_k is their lower envelope: when the
+// real-part maximum hops between the points of the peak top, two minima a fraction of a degree apart exist and the lower one
+// may belong to a neighbouring branch) and report the TRUE objective at their branch minimum.  All roles run in parallel.
+constexpr int POLISH_ROLES = 3;
+
 __global__ void __launch_bounds__(SEARCH_THREADS) search_polish_kernel(const __grid_constant__ PolishParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sp = reinterpret_cast<float2*>(smem_raw);
     __shared__ PolishShared sh;
+    __shared__ float amax_v[SEARCH_THREADS / 32];
+    __shared__ int amax_i[SEARCH_THREADS / 32];
     const int n = p.n;
     const int chunk = (n + SEARCH_THREADS - 1) / SEARCH_THREADS;
     const int padshift = ilog2_ceil(chunk);
     load_padded(sp, p.spec, n, padshift);
-    // the (blockIdx+1)-th best candidate that is distinct from all better ones (block_argmin's barriers also publish `sp`)
+    const double pu0 = p.gd != nullptr ? p.gd->u0 : p.u0;
+    const int start = int(blockIdx.x) / POLISH_ROLES, role = int(blockIdx.x) % POLISH_ROLES;
+    // the (start+1)-th best candidate that is distinct from all better ones (block_argmin's barriers also publish `sp`)
     Cand chosen[ZOOM_MAX_STARTS];
     Cand centre = block_argmin(p.prev, p.n_prev);
-    for (int s = 1; s <= int(blockIdx.x); ++s) {
+    for (int s = 1; s <= start; ++s) {
         chosen[s - 1] = centre;
         centre = block_argmin(p.prev, p.n_prev, chosen, s, p.sep0, p.sep1);
     }
+    // first index of the |S| maximum (the peak top the real-part maximum lives on)
+    int kmax = 0;
+    if (role != 0) {
+        float bv = -1.f;
+        int bi = 0x7fffffff;
+        for (int m = threadIdx.x; m < n; m += SEARCH_THREADS) {
+            const float2 x = sp[m + (m >> padshift)];
+            const float v = x.x * x.x + x.y * x.y;
+            if (v > bv) { bv = v; bi = m; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if ((threadIdx.x & 31) == 0) { amax_v[threadIdx.x >> 5] = bv; amax_i[threadIdx.x >> 5] = bi; }
+        __syncthreads();
+        bv = amax_v[0]; bi = amax_i[0];
+        for (int w = 1; w < SEARCH_THREADS / 32; ++w)
+            if (amax_v[w] > bv || (amax_v[w] == bv && amax_i[w] < bi)) { bv = amax_v[w]; bi = amax_i[w]; }
+        kmax = bi;
+    }
+    const int frozen = role == 0 ? -1 : kmax + (role == 1 ? -1 : 1);
     Cand res;
     res.f = CUDART_INF; res.p0 = centre.p0; res.p1 = centre.p1; res.pad = 0;
-    if (centre.f < CUDART_INF) {             // (uniform over the CTA)
+    if (centre.f < CUDART_INF && (role == 0 || (frozen >= 0 && frozen < n))) {             // (uniform over the CTA)
         const int m0 = min(int(threadIdx.x) * chunk, n), m1 = min(m0 + chunk, n);
         double x0 = centre.p0, x1 = centre.p1, fx = CUDART_INF;
         GradSums<double> sx;
-        polish_run(sp, padshift, n, p.u0, p.du, m0, m1, p, sh, -1, POLISH_MAXIT, x0, x1, fx, sx);
-        // kink hop: f = min_k A/(N d_k) over the points k that can hold max(d); try the two neighbours of the current one
+        polish_run(sp, padshift, n, pu0, p.du, m0, m1, p, sh, frozen, POLISH_MAXIT, x0, x1, fx, sx);
         __shared__ double bx0, bx1, bf;
-        __shared__ int kstar;
-        if (threadIdx.x == 0) {
-            bx0 = x0; bx1 = x1; bf = fx;
-            kstar = int(llrint((sx.umax - p.u0) / p.du));
-        }
+        __shared__ int wall;
+        if (threadIdx.x == 0) { bx0 = x0; bx1 = x1; bf = fx; sh.y0 = x0; sh.y1 = x1; sh.frozen = -1; }
         __syncthreads();
-        if (bf < CUDART_INF) {
-            const int k0 = kstar;
-            bool improved = false;
-            for (int side = -1; side <= 1; side += 2) {
-                const int alt = k0 + side;
-                if (alt < 0 || alt >= n) continue;
-                double y0 = bx0, y1 = bx1, fy = CUDART_INF;
-                GradSums<double> sy;
-                __syncthreads();
-                polish_run(sp, padshift, n, p.u0, p.du, m0, m1, p, sh, alt, 4, y0, y1, fy, sy);
-                // the true objective (free maximum) at the branch minimum
-                if (threadIdx.x == 0) { sh.y0 = y0; sh.y1 = y1; sh.frozen = -1; }
-                __syncthreads();
-                FG r[3];
-                polish_eval(sp, padshift, n, p.u0, p.du, m0, m1, sh, r, nullptr);
-                __shared__ int better;
-                if (threadIdx.x == 0) {
-                    better = (r[0].f < bf) ? 1 : 0;
-                    if (better) { bx0 = y0; bx1 = y1; bf = r[0].f; }
-                }
-                __syncthreads();
-                improved = improved || (better != 0);
-            }
-            if (improved) {
-                double y0 = bx0, y1 = bx1, fy = CUDART_INF;
-                GradSums<double> sy;
-                polish_run(sp, padshift, n, p.u0, p.du, m0, m1, p, sh, -1, 4, y0, y1, fy, sy);
-                if (threadIdx.x == 0 && fy <= bf) { bx0 = y0; bx1 = y1; bf = fy; }
-                __syncthreads();
-            }
+        if (role != 0 && bf < CUDART_INF) {
+            // the true objective (free maximum) at the branch minimum
+            FG r[3];
+            polish_eval(sp, padshift, n, pu0, p.du, m0, m1, sh, r, nullptr);
+            if (threadIdx.x == 0) { bf = r[0].f; sh.H = r[0].H; sh.pen = r[0].pen; }
+            __syncthreads();
         }
         if (threadIdx.x == 0) {
+            // the penalty (almost) vanishes here: the optimum is CONSTRAINED by the wall 1000 P > 0 (or the entropy term's
+            // roughness decides) and the direct-search levels locate it (flag travels in Cand::pad)
+            wall = (bf < CUDART_INF && sh.pen < 4.0 * sh.H) ? 1 : 0;
             double w = fmod(bx0 + 180.0, 360.0);
             if (w < 0) w += 360.0;
-            res.f = bf; res.p0 = w - 180.0; res.p1 = bx1;
+            res.f = bf; res.p0 = w - 180.0; res.p1 = bx1; res.pad = double(wall);
             // never return something worse than the grid point the polish started from
-            if (!(res.f <= centre.f)) { res.f = centre.f; res.p0 = centre.p0; res.p1 = centre.p1; }
+            if (!(res.f <= centre.f)) { res.f = centre.f; res.p0 = centre.p0; res.p1 = centre.p1; res.pad = 1.0; }
         }
     }
     if (threadIdx.x == 0) p.out[blockIdx.x] = res;
 }
 
-// final pick: result = {p0, p1, f, 0}
-__global__ void search_finalize_kernel(const Cand* list, int n_list, double* result) {
+// final pick: result = {p0, p1, f, 0}; optionally the phase parameters of pass 2 (K1PhaseDev) so that the chain needs no host
+// read-back: turns(m) = a + b*m with a = p0/360 + (p1/360) u0, b = (p1/360) du  (phasing.py:56-69 on a uniform axis)
+struct FinalizePhase {
+    void* ph_out;              // K1PhaseDev* or null
+    const SearchGeomDev* gd;   // u0 from device memory (or null: u0 below)
+    double u0, du;
+    int n;                     // transform length (fold / step tables are per n/16 block)
+    int p0_only;
+};
+struct K1PhaseDevLayout {      // == xmr::K1PhaseDev (k1_fft.cuh); repeated here so that the search does not include the FFT
+    double ph_a_turns, ph_b_turns;
+    float2 ph_step[16];
+    float2 ph_fold[16];
+};
+__global__ void search_finalize_kernel(const Cand* list, int n_list, double* result, FinalizePhase fp) {
     const Cand b = block_argmin(list, n_list);
     if (threadIdx.x == 0) {
         result[0] = b.p0;
         result[1] = b.p1;
         result[2] = b.f;
         result[3] = 0.0;
+    }
+    if (fp.ph_out != nullptr && threadIdx.x < 16) {
+        K1PhaseDevLayout* ph = static_cast<K1PhaseDevLayout*>(fp.ph_out);
+        const double u0 = fp.gd != nullptr ? fp.gd->u0 : fp.u0;
+        const double p1 = fp.p0_only ? 0.0 : b.p1;
+        const double a = b.p0 / 360.0 + (p1 / 360.0) * u0, bt = (p1 / 360.0) * fp.du;
+        const int d = threadIdx.x, q = fp.n / 16;
+        double turns = bt * double(q) * double(d);
+        turns -= floor(turns);
+        double sn, cs;
+        sincospi(2.0 * turns, &sn, &cs);
+        ph->ph_step[d] = make_float2(float(cs), float(sn));
+        const long long m0 = ((long long)q * d + fp.n / 2) % fp.n;
+        double tf = a + bt * double(m0);
+        tf -= floor(tf);
+        sincospi(2.0 * tf, &sn, &cs);
+        ph->ph_fold[d] = make_float2(float(cs), float(sn));
+        if (d == 0) { ph->ph_a_turns = a; ph->ph_b_turns = bt; }
     }
 }
 

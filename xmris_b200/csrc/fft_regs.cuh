@@ -46,8 +46,33 @@ XMR_HD float cos32(int k) {
 }
 XMR_HD float sin32(int k) { return cos32((k + 24) & 31); }  // sin(x) = cos(x - pi/2)
 
+#if defined(__CUDA_ARCH__) && defined(XMR_PACKED_F32X2)
+// Blackwell packed FP32: one FADD2 adds both components of a complex number (same FP32 pipe time as two FADDs -- measured
+// tools/ubench/packed_fp32.cu: 36.9 vs 36.1 T results/s -- but ONE issue slot).
+__device__ __forceinline__ unsigned long long pack2(float2 a) {
+    unsigned long long u;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(u) : "f"(a.x), "f"(a.y));
+    return u;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long u) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(u));
+    return r;
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pack2(a)), "l"(pack2(b)));
+    return unpack2(r);
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pack2(a)), "l"(pack2(b)));
+    return unpack2(r);
+}
+#else
 XMR_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 XMR_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 XMR_HD float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }

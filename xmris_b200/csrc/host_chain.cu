@@ -7,12 +7,23 @@
 // Pageable buffers are page-locked for the duration of the call (cudaHostRegister) so that the copies are truly
 // asynchronous; already pinned buffers are used as they are.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <vector>
 
 #include "../../include/xmris_b200.h"
 #include "abi_common.h"
+
+namespace xmr_abi {
+int k1_dispatch(const void* fid_dev, void* spec_dev, int64_t batch, int n_in, int n_out, int pad_left, int window_mode,
+                const float* window_dev, const float* win_rows_host, float scale, int inverse, int in_shift, int out_shift,
+                float* absmax_dev, int* argmax_dev, int phase_mode, double ph_a_turns, double ph_b_turns, float* run_max2,
+                const long long* row_flat_dev, const void* ph_dev, void* stream);                        // xmris_abi.cu
+int autophase_search_dev(const void* spec_dev, int n, double du, int method, const int* pivot_dev, int fixed_pivot, double u0_fixed,
+                         int fixed_target, int index_width, int p0_only, double* result_dev, void* workspace_dev, void* ph_out,
+                         void* stream);                                                                  // autophase_abi.cu
+}  // namespace xmr_abi
 
 namespace {
 
@@ -120,6 +131,8 @@ bool split_window(const double* w, int n, std::vector<float>& cols, std::vector<
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+std::atomic<long long> g_graph_launches{0};
 
 }  // namespace
 
@@ -327,9 +340,11 @@ int xmr_chain_host_c64(const xmr_host_chain_desc* d, const void* fid_host, void*
 // (what the survey's proposed `xmr_autophase_c64(fid, out, ..., mode=single)` asks for: pass 1 with branch and bound ->
 // global argmax -> the winning spectrum -> (p0, p1) search -> pass 2 with the fused phase; three small device->host reads,
 // no host code between the launches but the winner bookkeeping.)
+int64_t xmr_chain_single_graph_launches(void) { return g_graph_launches.load(); }
+
 int64_t xmr_chain_single_workspace_bytes(int64_t batch, int n_out) {
     if (batch < 0 || n_out < 1) return 0;
-    return int64_t(align_up(size_t(batch) * 4, 256) + 256 + align_up(size_t(n_out) * 8 + 64, 256) +
+    return int64_t(align_up(size_t(batch) * 4, 256) + 256 + 512 + align_up(size_t(n_out) * 8 + 64, 256) +
                    size_t(xmr_autophase_workspace_bytes()));
 }
 
@@ -346,61 +361,135 @@ int xmr_chain_single_dev_c64(const xmr_host_chain_desc* d, const void* fid_dev, 
     if (!fid_dev || !spec_dev || !workspace_dev || !result_host) return xmr_abi::fail(XMR_ERR_BAD_ARG, "NULL pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned char* sm = static_cast<unsigned char*>(workspace_dev);
-    const size_t o_arg = align_up(size_t(batch) * 4, 256);       // 16 B argmax record | running max at +32 | search result at +64
-    const size_t o_row = o_arg + 256;                             // one spectrum + its stats
+    // control block (256 B): global argmax record {float max @0, int64 flat @8} | running max @32 | search result double[4] @64 |
+    // winning row's {|S| max float @128, argmax int @144};  then the phase parameters of pass 2, the winning spectrum, search scratch
+    const size_t o_arg = align_up(size_t(batch) * 4, 256);
+    const size_t o_ph = o_arg + 256;
+    const size_t o_row = o_ph + 512;
     const size_t o_sws = o_row + align_up(size_t(n_out) * 8 + 64, 256);
     float* absmax = reinterpret_cast<float*>(sm);
     const float scale = d->scale != 0.f ? d->scale : 1.0f / std::sqrt(float(n_out));
     float ones[32];
     for (float& r : ones) r = 1.0f;
     const float* rows = win_rows_host ? win_rows_host : ones;
-    const size_t row_in = size_t(n_in) * 8, row_out = size_t(n_out) * 8;
     int rc;
 #define XMR_RC(call)                  \
     do {                              \
         rc = (call);                  \
         if (rc != XMR_OK) return rc;  \
     } while (0)
-    XMR_RC(xmr_fid_absmax_pruned_c64(fid_dev, batch, n_in, n_out, d->pad_left, window_mode, window_dev, rows, scale, absmax,
-                                     reinterpret_cast<float*>(sm + o_arg + 32), 1, st));
-    XMR_RC(xmr_global_argmax(absmax, nullptr, batch, n_out, sm + o_arg, st));
-    unsigned char arg_h[16];
-    XMR_CU(cudaMemcpyAsync(arg_h, sm + o_arg, 16, cudaMemcpyDeviceToHost, st));
-    XMR_CU(cudaStreamSynchronize(st));
+    // Everything between the two passes takes its inputs from device memory: the winning row (global argmax record), the pivot
+    // (the winner's own argmax) and the phase parameters of pass 2 (written by the search's final kernel).  Nothing is read
+    // back before pass 2 is enqueued.  The ~13 launches up to the search's final kernel (+ the 256-byte control block's
+    // copy to pinned host memory) are captured ONCE per argument set into a CUDA graph and replayed: small batches are
+    // launch-bound otherwise (C2: 4096 x 2048 spends more time between its kernels than in them).
+    float* absmax_p = absmax;
+    auto enqueue_front = [&](cudaStream_t s, unsigned char* ctl_pinned) -> int {
+        XMR_RC(xmr_fid_absmax_pruned_c64(fid_dev, batch, n_in, n_out, d->pad_left, window_mode, window_dev, rows, scale, absmax_p,
+                                         reinterpret_cast<float*>(sm + o_arg + 32), 1, s));
+        XMR_RC(xmr_global_argmax(absmax_p, nullptr, batch, n_out, sm + o_arg, s));
+        unsigned char* rowbuf = sm + o_row;
+        float* row_abs = reinterpret_cast<float*>(sm + o_arg + 128);
+        int* row_arg = reinterpret_cast<int*>(sm + o_arg + 144);
+        XMR_RC(xmr_abi::k1_dispatch(fid_dev, rowbuf, 1, n_in, n_out, d->pad_left, window_mode, window_dev, rows, scale, 0, 0, n_out / 2,
+                                    row_abs, row_arg, XMR_PHASE_NONE, 0.0, 0.0, nullptr,
+                                    reinterpret_cast<const long long*>(sm + o_arg + 8), nullptr, s));
+        double* res = reinterpret_cast<double*>(sm + o_arg + 64);
+        XMR_RC(xmr_abi::autophase_search_dev(rowbuf, n_out, d->du, d->method, row_arg, d->fixed_pivot, d->u0_fixed, d->fixed_target,
+                                             d->index_width > 0 ? d->index_width : 1, d->p0_only, res, sm + o_sws, sm + o_ph, s));
+        XMR_CU(cudaMemcpyAsync(ctl_pinned, sm + o_arg, 256, cudaMemcpyDeviceToHost, s));
+        return XMR_OK;
+    };
+    // per-thread state: pinned landing buffer, completion event, capture stream, a small graph cache
+    struct GraphEntry {
+        unsigned char key[160];
+        int seen = 0;
+        cudaGraphExec_t exec = nullptr;
+    };
+    static thread_local unsigned char* ctl_pinned = nullptr;
+    static thread_local cudaEvent_t searched = nullptr;
+    static thread_local cudaStream_t cap = nullptr;
+    static thread_local int state_dev = -1;
+    static thread_local GraphEntry cache[4];
+    static thread_local int cache_next = 0;
+    int dev = 0;
+    XMR_CU(cudaGetDevice(&dev));
+    if (state_dev != dev) {
+        if (ctl_pinned) { cudaFreeHost(ctl_pinned); cudaEventDestroy(searched); cudaStreamDestroy(cap); }
+        for (GraphEntry& e : cache) { if (e.exec) cudaGraphExecDestroy(e.exec); e = GraphEntry(); }
+        XMR_CU(cudaMallocHost(reinterpret_cast<void**>(&ctl_pinned), 256));
+        XMR_CU(cudaEventCreateWithFlags(&searched, cudaEventDisableTiming));
+        XMR_CU(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+        state_dev = dev;
+    }
+    unsigned char key[160];
+    std::memset(key, 0, sizeof(key));
+    {
+        size_t o = 0;
+        auto put = [&](const void* v, size_t nbytes) { std::memcpy(key + o, v, nbytes); o += nbytes; };
+        put(&fid_dev, 8); put(&workspace_dev, 8); put(&window_dev, 8); put(&batch, 8);
+        put(&n_in, 4); put(&n_out, 4); put(&d->pad_left, 4); put(&window_mode, 4); put(&scale, 4);
+        put(&d->method, 4); put(&d->index_width, 4); put(&d->p0_only, 4); put(&d->fixed_pivot, 4); put(&d->fixed_target, 4);
+        put(&d->u0_fixed, 8); put(&d->du, 8);
+        float rsum[2] = {0.f, 0.f};                              // the row factors travel by value into the kernel parameters
+        for (int i = 0; i < 32; ++i) { rsum[0] += rows[i] * float(i + 1); rsum[1] += rows[i] * rows[i]; }
+        put(rsum, 8);
+    }
+    GraphEntry* ent = nullptr;
+    for (GraphEntry& e : cache)
+        if (e.seen && std::memcmp(e.key, key, sizeof(key)) == 0) ent = &e;
+    bool launched = false;
+    if (ent != nullptr && ent->exec == nullptr && ent->seen == 1) {
+        // second call with these arguments (tables and kernel attributes exist now): capture
+        ent->seen = 2;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int crc = enqueue_front(cap, ctl_pinned);
+            const cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+            if (crc == XMR_OK && ce == cudaSuccess && graph != nullptr) {
+                if (cudaGraphInstantiate(&ent->exec, graph, 0) != cudaSuccess) ent->exec = nullptr;
+            }
+            if (graph) cudaGraphDestroy(graph);
+        }
+        cudaGetLastError();     // a failed capture leaves the eager path below (same kernels, same stream order)
+    }
+    if (ent != nullptr && ent->exec != nullptr) {
+        XMR_CU(cudaGraphLaunch(ent->exec, st));
+        launched = true;
+        ++g_graph_launches;
+    }
+    if (!launched) {
+        XMR_RC(enqueue_front(st, ctl_pinned));
+        if (ent == nullptr) {
+            GraphEntry& e = cache[cache_next];
+            cache_next = (cache_next + 1) % 4;
+            if (e.exec) cudaGraphExecDestroy(e.exec);
+            e = GraphEntry();
+            std::memcpy(e.key, key, sizeof(key));
+            e.seen = 1;
+        }
+    }
+    XMR_CU(cudaEventRecord(searched, st));
+    XMR_RC(xmr_abi::k1_dispatch(fid_dev, spec_dev, batch, n_in, n_out, d->pad_left, window_mode, window_dev, rows, scale, 0, 0, n_out / 2,
+                                nullptr, nullptr, XMR_PHASE_UNIFORM, 0.0, 0.0, nullptr, nullptr, sm + o_ph, st));
+    XMR_CU(cudaEventSynchronize(searched));     // the control block has landed; pass 2 keeps running
+#undef XMR_RC
+    unsigned char ctl[256];
+    std::memcpy(ctl, ctl_pinned, 256);
     float vmax;
     long long flat;
-    std::memcpy(&vmax, arg_h, 4);
-    std::memcpy(&flat, arg_h + 8, 8);
-    const long long row = flat / n_out;
-    unsigned char* rowbuf = sm + o_row;
-    float* row_abs = reinterpret_cast<float*>(rowbuf + row_out);
-    int* row_arg = reinterpret_cast<int*>(rowbuf + row_out + 16);
-    XMR_RC(xmr_fid_to_spectrum_c64(static_cast<const unsigned char*>(fid_dev) + size_t(row) * row_in, rowbuf, 1, n_in, n_out, d->pad_left,
-                                   window_mode, window_dev, rows, scale, 0, 0, n_out / 2, row_abs, row_arg, XMR_PHASE_NONE, 0.0, 0.0, st));
-    int idx = 0;
-    if (!d->fixed_pivot) {
-        XMR_CU(cudaMemcpyAsync(&idx, row_arg, 4, cudaMemcpyDeviceToHost, st));
-        XMR_CU(cudaStreamSynchronize(st));
-    }
-    const int target = d->fixed_pivot ? d->fixed_target : idx;
-    const double u0 = d->fixed_pivot ? d->u0_fixed : -d->du * double(idx);
-    double* res = reinterpret_cast<double*>(sm + o_arg + 64);
-    XMR_RC(xmr_autophase_search_c64(rowbuf, n_out, u0, d->du, d->method, target, d->index_width > 0 ? d->index_width : 1, d->p0_only, res,
-                                    sm + o_sws, st));
     double res_h[4];
-    XMR_CU(cudaMemcpyAsync(res_h, res, 32, cudaMemcpyDeviceToHost, st));
-    XMR_CU(cudaStreamSynchronize(st));
-    const double p0 = res_h[0], p1 = d->p0_only ? 0.0 : res_h[1];
-    result_host[0] = p0;
-    result_host[1] = p1;
-    result_host[2] = double(target);
+    int idx;
+    std::memcpy(&vmax, ctl, 4);
+    std::memcpy(&flat, ctl + 8, 8);
+    std::memcpy(res_h, ctl + 64, 32);
+    std::memcpy(&idx, ctl + 144, 4);
+    result_host[0] = res_h[0];
+    result_host[1] = d->p0_only ? 0.0 : res_h[1];
+    result_host[2] = double(d->fixed_pivot ? d->fixed_target : idx);
     result_host[3] = res_h[2];
     result_host[4] = double(vmax);
-    result_host[5] = double(row);
-    const double ph_a = p0 / 360.0 + (p1 / 360.0) * u0, ph_b = (p1 / 360.0) * d->du;
-    XMR_RC(xmr_fid_to_spectrum_c64(fid_dev, spec_dev, batch, n_in, n_out, d->pad_left, window_mode, window_dev, rows, scale, 0, 0, n_out / 2,
-                                   nullptr, nullptr, XMR_PHASE_UNIFORM, ph_a, ph_b, st));
-#undef XMR_RC
+    result_host[5] = double(flat / n_out);
     return XMR_OK;
 }
 

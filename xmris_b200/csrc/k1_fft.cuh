@@ -18,6 +18,14 @@ namespace xmr {
 constexpr int K1_STAGES = 2;
 
 
+// Phase parameters of the fused epilogue in DEVICE memory (written by search_finalize_kernel): lets pass 2 of the
+// mode="single" chain be enqueued before the search has finished -- no host read-back between the passes.
+struct K1PhaseDev {
+    double ph_a_turns, ph_b_turns;
+    float2 ph_step[16];
+    float2 ph_fold[16];
+};
+
 struct K1Params {
     const float2* in;
     float2* out;
@@ -38,6 +46,9 @@ struct K1Params {
     float2 ph_step[16];    // exp(2 pi i * b * R0*R1 * d), d < 16
     float2 ph_fold[16];    // folded-phase variants: exp(2 pi i (a + b * ((R0*R1*d + N/2) mod N))), d < 16
     float* run_max2;       // k1_max_kernel: running global max of |S|^2 (device scalar, zeroed by the launcher)
+    const long long* row_flat;   // generic kernel, optional: transform row (*row_flat / row_div) of `in` (device-resident winner)
+    int row_div;
+    const K1PhaseDev* ph_dev;    // optional: phase parameters from device memory instead of ph_* above
 };
 
 // N >= 8192: one shared buffer per spectrum serves as TMA landing slot, exchange A and exchange B ("in-place B"), one
@@ -78,7 +89,8 @@ __device__ __forceinline__ void amax_combine(float& v, int& i, float ov, int oi)
 //            zero rows of every stage-0 column are never loaded and the first butterfly layers degenerate), no left
 //            padding, no input rotation, out_shift == N/2, with the epilogue fixed at compile time (bit mask of
 //            K1_FAST_*): no per-element predicates or index arithmetic.
-enum : int { K1_FAST_ON = 1, K1_FAST_STORE = 2, K1_FAST_STATS = 4, K1_FAST_PHASE = 8, K1_FAST_ZF2 = 16, K1_FAST_ZF4 = 32 };
+enum : int { K1_FAST_ON = 1, K1_FAST_STORE = 2, K1_FAST_STATS = 4, K1_FAST_PHASE = 8, K1_FAST_ZF2 = 16, K1_FAST_ZF4 = 32,
+             K1_FAST_PHDEV = 64 /* store+phase variants: phase parameters read from p.ph_dev (shared-memory table) */ };
 
 // PRUNE (generic statistics-only launches with p.run_max2 set): branch and bound on the level-0 bound of k1_max.cuh,
 //            |X| <= sum_n |x_n w_n|, for ANY geometry (zero-filled input, N = 8192, table windows): a tile whose spectra
@@ -87,6 +99,7 @@ template <int N, bool INVERSE, int WIN, bool TMA, int FAST = 0, bool PRUNE = fal
 __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_kernel(const __grid_constant__ K1Params p) {
     static_assert(!PRUNE || (FAST == 0 && !INVERSE), "PRUNE is a variant of the generic forward statistics pass");
     __shared__ float run_s[2];   // PRUNE: thread 0's sample of the running maximum, double buffered by iteration parity
+    __shared__ float2 ph_tab[32];   // generic / PHDEV variants: ph_step[16] | ph_fold[16] (from p.ph_dev when given)
     using C = FftCfg<N>;
     constexpr bool F = (FAST != 0);
     constexpr int ZF = (FAST & K1_FAST_ZF4) ? 4 : ((FAST & K1_FAST_ZF2) ? 2 : 1);   // zero-fill factor of the fast variants
@@ -114,6 +127,22 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
     const int tid = threadIdx.x;
     const int g = tid / C::T;     // spectrum slot within the tile
     const int t = tid % C::T;     // thread within the spectrum
+    constexpr bool PHDEV = F && ((FAST & K1_FAST_PHDEV) != 0);
+    constexpr bool PH_TABLE = !F || PHDEV;          // the epilogue reads its step / fold phasors from shared memory
+    const float2* in_base = p.in;
+    if (!F && p.row_flat != nullptr) in_base += (*p.row_flat / p.row_div) * (long long)p.n_in;
+    double ph_a_turns = p.ph_a_turns, ph_b_turns = p.ph_b_turns;
+    if (PH_TABLE) {
+        if (p.ph_dev != nullptr) {
+            ph_a_turns = p.ph_dev->ph_a_turns;
+            ph_b_turns = p.ph_dev->ph_b_turns;
+        }
+        if (tid < 32) {
+            ph_tab[tid] = p.ph_dev != nullptr ? (tid < 16 ? p.ph_dev->ph_step[tid] : p.ph_dev->ph_fold[tid - 16])
+                                              : (tid < 16 ? p.ph_step[tid] : p.ph_fold[tid - 16]);
+        }
+        // (published by the block barriers that precede the first epilogue)
+    }
 
     const long long ntiles = (p.batch + C::SPB - 1) / C::SPB;
     const int n_in = F ? C::N / ZF : p.n_in;
@@ -138,7 +167,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
     if (FOLD) {
 #pragma unroll
         for (int k1 = 1; k1 < C::R0; ++k1) {
-            double turns = p.ph_b_turns * double(k1);
+            double turns = ph_b_turns * double(k1);
             turns -= floor(turns);
             double s, c;
             sincospi(2.0 * turns, &s, &c);
@@ -157,7 +186,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
 #pragma unroll
         for (int j = 0; j < C::C2; ++j) {
             const int q = t + C::T * j;
-            double turns = p.ph_a_turns + p.ph_b_turns * double(q);
+            double turns = ph_a_turns + ph_b_turns * double(q);
             turns -= floor(turns);
             double s, c;
             sincospi(2.0 * turns, &s, &c);
@@ -173,9 +202,9 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
         mbar_arrive_expect_tx(&bars[slot], row_bytes * nvalid);
         float2* dst = ring + size_t(slot) * C::SPB * SLOT;
         if (n_in == C::N && SLOT == size_t(C::N)) {
-            bulk_g2s(dst, p.in + s0 * n_in, row_bytes * nvalid, &bars[slot]);
+            bulk_g2s(dst, in_base + s0 * n_in, row_bytes * nvalid, &bars[slot]);
         } else {
-            for (int r = 0; r < nvalid; ++r) bulk_g2s(dst + size_t(r) * SLOT, p.in + (s0 + r) * n_in, row_bytes, &bars[slot]);
+            for (int r = 0; r < nvalid; ++r) bulk_g2s(dst + size_t(r) * SLOT, in_base + (s0 + r) * n_in, row_bytes, &bars[slot]);
         }
     };
 
@@ -186,7 +215,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
             float2 w = p.twN[(b * c * C::R0) % C::N];
             if (INVERSE) w.y = -w.y;
             if (FOLD) {
-                double turns = p.ph_b_turns * double(C::R0 * c);
+                double turns = ph_b_turns * double(C::R0 * c);
                 turns -= floor(turns);
                 double sn, cs;
                 sincospi(2.0 * turns, &sn, &cs);
@@ -227,7 +256,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
             __syncthreads();   // previous tile's readers of this slot are done
             for (int idx = tid; idx < nvalid * n_in; idx += C::THREADS) {
                 const int r = idx / n_in, k = idx - r * n_in;
-                ring[(size_t(slot) * C::SPB + r) * SLOT + k] = p.in[(s0 + r) * n_in + k];
+                ring[(size_t(slot) * C::SPB + r) * SLOT + k] = in_base[(s0 + r) * n_in + k];
             }
             __syncthreads();
         }
@@ -361,10 +390,10 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
                     const int m = F ? t + (kc >= NH ? kc - NH : kc + NH) : ((k + out_shift) & (C::N - 1));
                     float2 x = v[j * C::R2 + d];
                     if (FOLD) {
-                        x = cmul(x, p.ph_fold[d]);
+                        x = cmul(x, PHDEV ? ph_tab[16 + d] : p.ph_fold[d]);
                     } else if (do_phase) {
                         // m = q + Q*d' with d' = m / Q: rot = base(q) * step(d')
-                        const float2 r = cmul(ph_base[j], p.ph_step[(m / Q) & 15]);
+                        const float2 r = cmul(ph_base[j], PH_TABLE ? ph_tab[(m / Q) & 15] : p.ph_step[(m / Q) & 15]);
                         x = cmul(x, r);
                     }
                     st_stream(dst + m, x);

@@ -91,14 +91,17 @@ cudaError_t XMR_CAT(k1_launch_, XMR_N)(const K1Params& p, bool inverse, int win,
         return tma ? launch_one<XMR_N, true, 2, true>(p, max_ctas, st) : launch_one<XMR_N, true, 2, false>(p, max_ctas, st);
     }
     // hot path: full-length input, separable window, TMA, fftshift store -> compile-time epilogue variants
-    const bool fast_geom = tma && win == 2 && p.n_in == XMR_N && p.pad_left == 0 && p.in_shift == 0 &&
+    const bool fast_geom = p.row_flat == nullptr && tma && win == 2 && p.n_in == XMR_N && p.pad_left == 0 && p.in_shift == 0 &&
                            p.out_shift == XMR_N / 2 && XMR_N >= 512;
     if (fast_geom) {
         const bool st_ = p.out != nullptr, stats = p.absmax != nullptr && p.argmax == nullptr, ph = p.phase_on != 0;
         if (st_ && !stats && !ph && p.absmax == nullptr)
             return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE>(p, max_ctas, st);
-        if (st_ && ph && p.absmax == nullptr)
+        if (st_ && ph && p.absmax == nullptr) {
+            if (p.ph_dev != nullptr)
+                return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE | K1_FAST_PHASE | K1_FAST_PHDEV>(p, max_ctas, st);
             return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE | K1_FAST_PHASE>(p, max_ctas, st);
+        }
 #if XMR_N >= 512 && XMR_N <= 4096
         constexpr bool HAS_MAX_KERNEL = true;
 #else
@@ -130,12 +133,16 @@ cudaError_t XMR_CAT(k1_launch_, XMR_N)(const K1Params& p, bool inverse, int win,
     if (tma && win == 2 && p.pad_left == 0 && p.in_shift == 0 && p.out_shift == XMR_N / 2 && p.out != nullptr &&
         p.absmax == nullptr) {
         if (2 * p.n_in == XMR_N) {
+            if (p.phase_on != 0 && p.ph_dev != nullptr)
+                return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE | K1_FAST_PHASE | K1_FAST_ZF2 | K1_FAST_PHDEV>(p, max_ctas, st);
             if (p.phase_on != 0)
                 return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE | K1_FAST_PHASE | K1_FAST_ZF2>(p, max_ctas, st);
             return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE | K1_FAST_ZF2>(p, max_ctas, st);
         }
 #if XMR_N >= 1024
         if (4 * p.n_in == XMR_N) {
+            if (p.phase_on != 0 && p.ph_dev != nullptr)
+                return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE | K1_FAST_PHASE | K1_FAST_ZF4 | K1_FAST_PHDEV>(p, max_ctas, st);
             if (p.phase_on != 0)
                 return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE | K1_FAST_PHASE | K1_FAST_ZF4>(p, max_ctas, st);
             return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE | K1_FAST_ZF4>(p, max_ctas, st);

@@ -184,10 +184,16 @@ extern "C" {
 int xmr_version(void) { return 100; }
 const char* xmr_last_error(void) { return xmr_abi::g_err; }
 
-static int k1_dispatch(const void* fid_dev, void* spec_dev, int64_t batch, int n_in, int n_out, int pad_left,
-                       int window_mode, const float* window_dev, const float* win_rows_host, float scale,
-                       int inverse, int in_shift, int out_shift, float* absmax_dev, int* argmax_dev,
-                       int phase_mode, double ph_a_turns, double ph_b_turns, float* run_max2, void* stream) {
+}  // extern "C"
+
+namespace xmr_abi {
+// row_flat_dev (optional): transform row (*row_flat_dev / n_out) of fid_dev (batch must be 1);
+// ph_dev (optional, phase_mode = XMR_PHASE_UNIFORM): xmr::K1PhaseDev in device memory instead of ph_a_turns / ph_b_turns
+int k1_dispatch(const void* fid_dev, void* spec_dev, int64_t batch, int n_in, int n_out, int pad_left,
+                int window_mode, const float* window_dev, const float* win_rows_host, float scale,
+                int inverse, int in_shift, int out_shift, float* absmax_dev, int* argmax_dev,
+                int phase_mode, double ph_a_turns, double ph_b_turns, float* run_max2, const long long* row_flat_dev,
+                const void* ph_dev, void* stream) {
     if (!supported_n(n_out))
         return fail(XMR_ERR_UNSUPPORTED_N, "n_out=%d: transform length must be a power of two in [16, 8192]", n_out);
     if (batch < 0 || n_in < 1 || n_in > n_out || pad_left < 0 || pad_left + n_in > n_out)
@@ -230,6 +236,10 @@ static int k1_dispatch(const void* fid_dev, void* spec_dev, int64_t batch, int n
     p.absmax = absmax_dev;
     p.argmax = argmax_dev;
     p.run_max2 = run_max2;
+    p.row_flat = row_flat_dev;
+    p.row_div = n_out;
+    p.ph_dev = static_cast<const xmr::K1PhaseDev*>(ph_dev);
+    if (row_flat_dev != nullptr && batch != 1) return fail(XMR_ERR_BAD_ARG, "row_flat_dev needs batch == 1");
     const int r0 = n_out >= 256 ? n_out / 256 : 1;
     for (int i = 0; i < 32; ++i) p.win_rows[i] = 1.0f;
     int win = 2;
@@ -269,13 +279,17 @@ static int k1_dispatch(const void* fid_dev, void* spec_dev, int64_t batch, int n
     if (e != cudaSuccess) return cuda_fail(e, "k1 launch");
     return XMR_OK;
 }
+}  // namespace xmr_abi
+
+extern "C" {
+using xmr_abi::k1_dispatch;
 
 int xmr_fid_to_spectrum_c64(const void* fid_dev, void* spec_dev, int64_t batch, int n_in, int n_out, int pad_left,
                             int window_mode, const float* window_dev, const float* win_rows_host, float scale,
                             int inverse, int in_shift, int out_shift, float* absmax_dev, int* argmax_dev,
                             int phase_mode, double ph_a_turns, double ph_b_turns, void* stream) {
     return k1_dispatch(fid_dev, spec_dev, batch, n_in, n_out, pad_left, window_mode, window_dev, win_rows_host, scale, inverse,
-                       in_shift, out_shift, absmax_dev, argmax_dev, phase_mode, ph_a_turns, ph_b_turns, nullptr, stream);
+                       in_shift, out_shift, absmax_dev, argmax_dev, phase_mode, ph_a_turns, ph_b_turns, nullptr, nullptr, nullptr, stream);
 }
 
 int xmr_fid_absmax_pruned_c64(const void* fid_dev, int64_t batch, int n_in, int n_out, int pad_left, int window_mode,
@@ -287,7 +301,7 @@ int xmr_fid_absmax_pruned_c64(const void* fid_dev, int64_t batch, int n_in, int 
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(running max)");
     }
     return k1_dispatch(fid_dev, nullptr, batch, n_in, n_out, pad_left, window_mode, window_dev, win_rows_host, scale, 0, 0,
-                       n_out / 2, absmax_dev, nullptr, XMR_PHASE_NONE, 0.0, 0.0, running_max2_dev, stream);
+                       n_out / 2, absmax_dev, nullptr, XMR_PHASE_NONE, 0.0, 0.0, running_max2_dev, nullptr, nullptr, stream);
 }
 
 int xmr_zero_fill_c64(const void* in_dev, void* out_dev, int64_t batch, int n_in, int n_out, int pad_left,
