@@ -197,6 +197,25 @@ int xmr_host_workspace_release(void);
 int64_t xmr_chain_single_workspace_bytes(int64_t batch, int n_out);
 /* diagnostic: how many calls of xmr_chain_single_dev_c64 replayed their captured CUDA graph (process-wide) */
 int64_t xmr_chain_single_graph_launches(void);
+/* {front part ms (pass 1 ... search's final kernel), pass 2 ms} of this thread's last device chain, from CUDA events recorded
+ * on the caller's stream (waits for that chain's pass 2). */
+int xmr_chain_single_last_timing(double* ms_out);
+
+/* The same chain split at its one exchange point, for voxels sharded over several GPUs (one process per GPU).  The reference's
+ * mode="single" needs the GLOBAL |S| argmax (phasing.py:229-231):
+ *   front  pass 1 on this rank's shard, then its candidate slot {best FID row, max |S|, global row = row + row_offset}
+ *          (xmr_chain_single_slot_bytes(n_in) bytes at slot_dev)
+ *   ---    ONE all-gather of the slots (torch.distributed / NCCL), nothing else crosses the GPUs
+ *   back   every rank picks the winner among the `world` gathered slots ON THE DEVICE (ties: lowest global row), transforms and
+ *          searches it redundantly (deterministic: identical angles on every rank) and runs pass 2 on its shard.
+ * No host read-back between the passes on any rank; result_host as xmr_chain_single_dev_c64 (winning row = global row). */
+int64_t xmr_chain_single_slot_bytes(int n_in);
+int xmr_chain_single_front_c64(const xmr_host_chain_desc* desc, const void* fid_dev, int64_t batch, int window_mode,
+                               const float* window_dev, const float* win_rows_host, void* workspace_dev, int64_t row_offset,
+                               void* slot_dev, void* stream);
+int xmr_chain_single_back_c64(const xmr_host_chain_desc* desc, const void* fid_dev, void* spec_dev, int64_t batch,
+                              int window_mode, const float* window_dev, const float* win_rows_host, void* workspace_dev,
+                              const void* gathered_dev, int world, double* result_host, void* stream);
 int xmr_chain_single_dev_c64(const xmr_host_chain_desc* desc, const void* fid_dev, void* spec_dev, int64_t batch,
                              int window_mode, const float* window_dev, const float* win_rows_host, void* workspace_dev,
                              double* result_host, void* stream);

@@ -283,3 +283,53 @@ def test_chain_geometry_is_memoised_and_read_only():
     np.testing.assert_array_equal(a["freqs"], np.roll(np.fft.fftfreq(2048, d=t[1] - t[0]), 1024))
     with pytest.raises(ValueError, match="position"):
         chain.chain_geometry(1024, t, 2048, "middle", 5.0)
+
+
+def _slot_gather_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    from xmris_b200 import sharding
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        n_in = 31                                             # odd length: the slot is padded to an even row
+        rng = np.random.default_rng(5 + rank)
+        row = (rng.standard_normal(n_in) + 1j * rng.standard_normal(n_in)).astype(np.complex64)
+        vmax = 7.5                                            # a tie: the lowest global row must win on every rank
+        global_row = 1000 - 10 * rank
+        slot = sharding.pack_slot(row, vmax, global_row)
+        assert len(slot) == sharding.slot_elems(n_in) == 34
+        send = torch.from_numpy(slot.view(np.uint8).copy())
+        recv = torch.zeros((world, send.numel()), dtype=torch.uint8)
+        gather = sharding.SlotAllGather(dist)
+        assert gather.world_size == world
+        gather(recv, send)                                    # the ONE collective of the sharded chain
+        gathered = recv.numpy().view(np.complex64).reshape(world, -1)
+        win, best, brow = sharding.select_winner(gathered)
+        q.put((rank, win, best, brow, bool(np.array_equal(gathered[rank, :n_in], row))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slot_all_gather_two_ranks_gloo():
+    """The sharded mode="single" exchange (sharding.SlotAllGather + the slot wire layout) on two gloo ranks: one collective,
+    every rank selects the same winner, ties resolve to the lowest global row."""
+    import multiprocessing as mp
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_slot_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[0] for r in res] == [0, 1]
+    for r in res:
+        assert r[1] == 1 and r[2] == 7.5 and r[3] == 990 and r[4]      # rank 1 holds the lower global row

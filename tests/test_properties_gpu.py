@@ -198,3 +198,51 @@ def test_device_chain_replays_a_cuda_graph_and_gives_the_same_result():
     for o, i in zip(outs[1:], infos[1:]):
         assert i["p0"] == infos[0]["p0"] and i["p1"] == infos[0]["p1"] and i["pivot"] == infos[0]["pivot"]
         assert torch.equal(o, outs[0])
+
+
+def test_sharded_chain_equals_the_one_call_chain():
+    """front -> all-gather -> back (xmr_chain_single_front_c64 / _back_c64, the multi-GPU split of the chain) on two "ranks"
+    emulated on one GPU (each half of the batch is a shard; the all-gather is a device copy): the same global winner, the same
+    angles and spectra as the one-call chain on the whole batch, on both ranks."""
+    import torch
+
+    from xmris_b200 import chain, sharding
+    from xmris_b200.synth import make_fids_torch
+
+    dev = torch.device("cuda:0")
+    fid, t = make_fids_torch("1H", 2001, 2048, dev, seed=31)
+    whole, _, winfo = chain.chain_single(fid, t, None, "end", 5.0, peak_width=100)
+    lo = [0, 1100]
+    hi = [1100, 2001]
+    slots = []
+
+    class Capture:                       # pass 1 of both shards first (collects their slots) ...
+        world_size = 2
+
+        def __call__(self, recv, send):
+            slots.append(send.clone())
+            raise StopIteration
+
+    for r in range(2):
+        try:
+            chain.chain_single(fid[lo[r]:hi[r]], t, None, "end", 5.0, peak_width=100, all_gather=Capture(), row_offset=lo[r])
+        except StopIteration:
+            pass
+    gathered = torch.stack(slots)
+    host = gathered.cpu().numpy().view(np.complex64).reshape(2, -1)
+    win, best, grow = sharding.select_winner(host)
+    assert grow == winfo["winning_row"] and abs(best - winfo["max_abs"]) <= 1e-6 * best
+
+    class Replay:                        # ... then the full chain per shard with the gathered slots
+        world_size = 2
+
+        def __call__(self, recv, send):
+            recv.copy_(gathered)
+
+    for r in range(2):
+        part, _, info = chain.chain_single(fid[lo[r]:hi[r]], t, None, "end", 5.0, peak_width=100, all_gather=Replay(),
+                                           row_offset=lo[r])
+        assert info["winning_row"] == winfo["winning_row"] and info["pivot"] == winfo["pivot"]
+        assert abs(info["p0"] - winfo["p0"]) < 2e-3 and abs(info["p1"] - winfo["p1"]) < 6e-3
+        err = (part - whole[lo[r]:hi[r]]).abs().max().item() / whole.abs().max().item()
+        assert err < 1e-4, err

@@ -45,6 +45,10 @@ SIGNATURES = {
     "xmr_row_absmax_c64": (_i, [_vp, _i64, _i, _vp, _vp, _vp]),
     "xmr_chain_single_workspace_bytes": (_i64, [_i64, _i]),
     "xmr_chain_single_graph_launches": (_i64, []),
+    "xmr_chain_single_last_timing": (_i, [_vp]),
+    "xmr_chain_single_slot_bytes": (_i64, [_i]),
+    "xmr_chain_single_front_c64": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "xmr_chain_single_back_c64": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "xmr_chain_single_dev_c64": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp]),
     "xmr_baseline_als_workspace_bytes": (_i64, [_i64, _i]),
     "xmr_baseline_als": (_i, [_vp, _i, _vp, _i64, _i, _d, _d, _i, _vp, _i64, _vp]),

@@ -149,18 +149,22 @@ def apply_pass(fid_t, geo, p0, p1, pivot, out=None):
 
 
 def chain_single(fid_t, time_coord, target_points=None, position="end", lb=None, method="acme", peak_width=0.5,
-                 target_coord=None, p0_only=False, autophase_lb=0.0, out=None, exchange=None, gb=None):
+                 target_coord=None, p0_only=False, autophase_lb=0.0, out=None, exchange=None, gb=None, all_gather=None,
+                 row_offset=0):
     """Full chain with the reference's ``mode="single"`` autophase on a ``[batch, n_in]`` device tensor.
 
-    ``exchange`` (optional) is a callable ``(local_max, local_flat_index, search_fn) -> (p0, p1, pivot, fun)`` used by
-    the multi-GPU path to pick the global winner across ranks; single-GPU callers leave it ``None``.
+    Multi-GPU (voxels sharded over ranks): pass ``all_gather=sharding.SlotAllGather(dist)`` and ``row_offset`` (first global
+    row of this rank's shard): ONE device-side all-gather of the ranks' candidate rows, no host round trip, every rank
+    searches the global winner redundantly.  ``exchange`` (legacy, host-mediated) is a callable
+    ``(local_max, local_flat_index, search_fn) -> (p0, p1, pivot, fun)``: two small collectives through the host.
     Returns ``(phased spectrum tensor, freqs float64, info dict)``.
     """
     n_in = fid_t.shape[-1]
     flat = fid_t.reshape(-1, n_in)
     geo = chain_geometry(n_in, time_coord, target_points, position, lb, gb)
-    if exchange is None and autophase_lb == 0 and geo["n_out"] in D.SUPPORTED_N and flat.shape[0] > 0:
-        return _chain_single_one_call(fid_t, flat, geo, method, peak_width, target_coord, p0_only, out)
+    if autophase_lb == 0 and geo["n_out"] in D.SUPPORTED_N and (flat.shape[0] > 0 or all_gather is not None) and (
+            exchange is None):
+        return _chain_single_one_call(fid_t, flat, geo, method, peak_width, target_coord, p0_only, out, all_gather, row_offset)
     vmax, findex = local_stats(flat, geo)
 
     def search():
@@ -173,7 +177,7 @@ def chain_single(fid_t, time_coord, target_points=None, position="end", lb=None,
     return spec, geo["freqs"], dict(p0=p0, p1=p1, pivot=pivot, fun=fun, n_out=geo["n_out"], pad_left=geo["pad_left"])
 
 
-def _chain_single_one_call(fid_t, flat, geo, method, peak_width, target_coord, p0_only, out):
+def _chain_single_one_call(fid_t, flat, geo, method, peak_width, target_coord, p0_only, out, all_gather=None, row_offset=0):
     """Single-GPU ``mode="single"`` chain through ``xmr_chain_single_dev_c64`` (one C call, three small read-backs)."""
     from .processing import _index_width
 
@@ -185,11 +189,12 @@ def _chain_single_one_call(fid_t, flat, geo, method, peak_width, target_coord, p
         fixed = ((freqs[0] - float(target_coord)) / x_range, int(np.argmin(np.abs(freqs - target_coord))))
     spec, res = D.chain_single_dev(flat, n_out, geo["pad_left"], _win(geo, flat.device), du, method,
                                    _index_width(freqs, peak_width), p0_only, fixed,
-                                   out=None if out is None else out.reshape(-1, n_out))
+                                   out=None if out is None else out.reshape(-1, n_out), all_gather=all_gather,
+                                   row_offset=row_offset)
     pivot = float(target_coord) if target_coord is not None else float(freqs[int(res[2])])
     spec = spec.reshape(tuple(fid_t.shape[:-1]) + (n_out,))
     return spec, freqs, dict(p0=res[0], p1=0.0 if p0_only else res[1], pivot=pivot, fun=res[3], n_out=n_out,
-                             pad_left=geo["pad_left"])
+                             pad_left=geo["pad_left"], max_abs=res[4], winning_row=int(res[5]))
 
 
 def chain_to_spectrum(fid_t, time_coord, target_points=None, position="end", lb=None, out=None, gb=None):

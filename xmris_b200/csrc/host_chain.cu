@@ -19,10 +19,13 @@ namespace xmr_abi {
 int k1_dispatch(const void* fid_dev, void* spec_dev, int64_t batch, int n_in, int n_out, int pad_left, int window_mode,
                 const float* window_dev, const float* win_rows_host, float scale, int inverse, int in_shift, int out_shift,
                 float* absmax_dev, int* argmax_dev, int phase_mode, double ph_a_turns, double ph_b_turns, float* run_max2,
-                const long long* row_flat_dev, const void* ph_dev, void* stream);                        // xmris_abi.cu
+                const long long* row_slot_dev, int row_stride, const void* ph_dev, void* stream);        // xmris_abi.cu
 int autophase_search_dev(const void* spec_dev, int n, double du, int method, const int* pivot_dev, int fixed_pivot, double u0_fixed,
                          int fixed_target, int index_width, int p0_only, double* result_dev, void* workspace_dev, void* ph_out,
                          void* stream);                                                                  // autophase_abi.cu
+int pack_winner(const void* fid_dev, int64_t batch, int n_in, int n_out, const void* arg_record_dev, int64_t row_offset,
+                void* slot_dev, void* stream);                                                           // xmris_abi.cu
+int select_winner(const void* gathered_dev, int world, int n_in, void* ctl_dev, void* stream);
 }  // namespace xmr_abi
 
 namespace {
@@ -342,86 +345,240 @@ int xmr_chain_host_c64(const xmr_host_chain_desc* d, const void* fid_host, void*
 // no host code between the launches but the winner bookkeeping.)
 int64_t xmr_chain_single_graph_launches(void) { return g_graph_launches.load(); }
 
+int64_t xmr_chain_single_slot_bytes(int n_in) { return n_in > 0 ? int64_t(((n_in + 1) & ~1) + 2) * 8 : 0; }
+
 int64_t xmr_chain_single_workspace_bytes(int64_t batch, int n_out) {
     if (batch < 0 || n_out < 1) return 0;
     return int64_t(align_up(size_t(batch) * 4, 256) + 256 + 512 + align_up(size_t(n_out) * 8 + 64, 256) +
-                   size_t(xmr_autophase_workspace_bytes()));
+                   align_up(size_t(n_out + 4) * 8, 256) + size_t(xmr_autophase_workspace_bytes()));
 }
 
-int xmr_chain_single_dev_c64(const xmr_host_chain_desc* d, const void* fid_dev, void* spec_dev, int64_t batch, int window_mode,
-                             const float* window_dev, const float* win_rows_host, void* workspace_dev, double* result_host,
-                             void* stream) {
+}  // extern "C"
+
+namespace {
+
+struct ChainLayout {
+    size_t o_arg, o_ph, o_row, o_slot, o_sws;
+    ChainLayout(int64_t batch, int n_out) {
+        o_arg = align_up(size_t(batch) * 4, 256);     // control block (256 B), see chain_back
+        o_ph = o_arg + 256;                            // K1PhaseDev of pass 2
+        o_row = o_ph + 512;                            // the winning spectrum
+        o_slot = o_row + align_up(size_t(n_out) * 8 + 64, 256);   // this rank's candidate slot (single-GPU: the gathered buffer)
+        o_sws = o_slot + align_up(size_t(n_out + 4) * 8, 256);    // search scratch
+    }
+};
+
+int check_chain_args(const xmr_host_chain_desc* d, int64_t batch) {
     if (!d) return xmr_abi::fail(XMR_ERR_BAD_ARG, "descriptor is NULL");
     const int n_in = d->n_in, n_out = d->n_out;
     if (batch < 0 || n_in < 1 || n_out < n_in || d->pad_left < 0 || d->pad_left + n_in > n_out)
         return xmr_abi::fail(XMR_ERR_BAD_ARG, "bad sizes: batch=%lld n_in=%d n_out=%d pad_left=%d", (long long)batch, n_in, n_out, d->pad_left);
     if (!(n_out >= 16 && n_out <= 8192 && (n_out & (n_out - 1)) == 0))
         return xmr_abi::fail(XMR_ERR_UNSUPPORTED_N, "n_out=%d: the device chain needs a power-of-two length in [16, 8192]", n_out);
-    if (batch == 0) return XMR_OK;
-    if (!fid_dev || !spec_dev || !workspace_dev || !result_host) return xmr_abi::fail(XMR_ERR_BAD_ARG, "NULL pointer");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    unsigned char* sm = static_cast<unsigned char*>(workspace_dev);
-    // control block (256 B): global argmax record {float max @0, int64 flat @8} | running max @32 | search result double[4] @64 |
-    // winning row's {|S| max float @128, argmax int @144};  then the phase parameters of pass 2, the winning spectrum, search scratch
-    const size_t o_arg = align_up(size_t(batch) * 4, 256);
-    const size_t o_ph = o_arg + 256;
-    const size_t o_row = o_ph + 512;
-    const size_t o_sws = o_row + align_up(size_t(n_out) * 8 + 64, 256);
-    float* absmax = reinterpret_cast<float*>(sm);
-    const float scale = d->scale != 0.f ? d->scale : 1.0f / std::sqrt(float(n_out));
-    float ones[32];
-    for (float& r : ones) r = 1.0f;
-    const float* rows = win_rows_host ? win_rows_host : ones;
-    int rc;
+    return XMR_OK;
+}
+
 #define XMR_RC(call)                  \
     do {                              \
         rc = (call);                  \
         if (rc != XMR_OK) return rc;  \
     } while (0)
-    // Everything between the two passes takes its inputs from device memory: the winning row (global argmax record), the pivot
-    // (the winner's own argmax) and the phase parameters of pass 2 (written by the search's final kernel).  Nothing is read
-    // back before pass 2 is enqueued.  The ~13 launches up to the search's final kernel (+ the 256-byte control block's
-    // copy to pinned host memory) are captured ONCE per argument set into a CUDA graph and replayed: small batches are
-    // launch-bound otherwise (C2: 4096 x 2048 spends more time between its kernels than in them).
-    float* absmax_p = absmax;
-    auto enqueue_front = [&](cudaStream_t s, unsigned char* ctl_pinned) -> int {
-        XMR_RC(xmr_fid_absmax_pruned_c64(fid_dev, batch, n_in, n_out, d->pad_left, window_mode, window_dev, rows, scale, absmax_p,
-                                         reinterpret_cast<float*>(sm + o_arg + 32), 1, s));
-        XMR_RC(xmr_global_argmax(absmax_p, nullptr, batch, n_out, sm + o_arg, s));
-        unsigned char* rowbuf = sm + o_row;
-        float* row_abs = reinterpret_cast<float*>(sm + o_arg + 128);
-        int* row_arg = reinterpret_cast<int*>(sm + o_arg + 144);
-        XMR_RC(xmr_abi::k1_dispatch(fid_dev, rowbuf, 1, n_in, n_out, d->pad_left, window_mode, window_dev, rows, scale, 0, 0, n_out / 2,
-                                    row_abs, row_arg, XMR_PHASE_NONE, 0.0, 0.0, nullptr,
-                                    reinterpret_cast<const long long*>(sm + o_arg + 8), nullptr, s));
-        double* res = reinterpret_cast<double*>(sm + o_arg + 64);
-        XMR_RC(xmr_abi::autophase_search_dev(rowbuf, n_out, d->du, d->method, row_arg, d->fixed_pivot, d->u0_fixed, d->fixed_target,
-                                             d->index_width > 0 ? d->index_width : 1, d->p0_only, res, sm + o_sws, sm + o_ph, s));
-        XMR_CU(cudaMemcpyAsync(ctl_pinned, sm + o_arg, 256, cudaMemcpyDeviceToHost, s));
-        return XMR_OK;
-    };
-    // per-thread state: pinned landing buffer, completion event, capture stream, a small graph cache
-    struct GraphEntry {
-        unsigned char key[160];
-        int seen = 0;
-        cudaGraphExec_t exec = nullptr;
-    };
-    static thread_local unsigned char* ctl_pinned = nullptr;
-    static thread_local cudaEvent_t searched = nullptr;
-    static thread_local cudaStream_t cap = nullptr;
-    static thread_local int state_dev = -1;
-    static thread_local GraphEntry cache[4];
-    static thread_local int cache_next = 0;
+
+// pass 1 (branch and bound) -> this shard's argmax record -> candidate slot {best FID row, max |S|, global row}
+int chain_front(const xmr_host_chain_desc* d, const void* fid_dev, int64_t batch, int window_mode, const float* window_dev,
+                const float* rows, float scale, unsigned char* sm, int64_t row_offset, void* slot_dev, cudaStream_t st) {
+    const ChainLayout L(batch, d->n_out);
+    float* absmax = reinterpret_cast<float*>(sm);
+    int rc;
+    if (batch > 0) {
+        XMR_RC(xmr_fid_absmax_pruned_c64(fid_dev, batch, d->n_in, d->n_out, d->pad_left, window_mode, window_dev, rows, scale, absmax,
+                                         reinterpret_cast<float*>(sm + L.o_arg + 32), 1, st));
+        XMR_RC(xmr_global_argmax(absmax, nullptr, batch, d->n_out, sm + L.o_arg, st));
+    }
+    return xmr_abi::pack_winner(fid_dev, batch, d->n_in, d->n_out, sm + L.o_arg, row_offset, slot_dev, st);
+}
+
+// global winner among `world` gathered slots -> its spectrum + pivot -> (p0, p1) search -> phase parameters (device) ->
+// 256-byte control block to pinned host memory.   Control block: {float max @0, int64 winning slot @8, int64 global row @16,
+// running max @32, search result double[4] @64, winner's |S| max float @128, its argmax int @144}
+int chain_mid(const xmr_host_chain_desc* d, int64_t batch, int window_mode, const float* window_dev, const float* rows, float scale,
+              unsigned char* sm, const void* gathered_dev, int world, unsigned char* ctl_pinned, cudaStream_t st) {
+    const ChainLayout L(batch, d->n_out);
+    const int n_in = d->n_in, n_out = d->n_out;
+    int rc;
+    XMR_RC(xmr_abi::select_winner(gathered_dev, world, n_in, sm + L.o_arg, st));
+    unsigned char* rowbuf = sm + L.o_row;
+    float* row_abs = reinterpret_cast<float*>(sm + L.o_arg + 128);
+    int* row_arg = reinterpret_cast<int*>(sm + L.o_arg + 144);
+    XMR_RC(xmr_abi::k1_dispatch(gathered_dev, rowbuf, 1, n_in, n_out, d->pad_left, window_mode, window_dev, rows, scale, 0, 0, n_out / 2,
+                                row_abs, row_arg, XMR_PHASE_NONE, 0.0, 0.0, nullptr,
+                                reinterpret_cast<const long long*>(sm + L.o_arg + 8), ((n_in + 1) & ~1) + 2, nullptr, st));
+    double* res = reinterpret_cast<double*>(sm + L.o_arg + 64);
+    XMR_RC(xmr_abi::autophase_search_dev(rowbuf, n_out, d->du, d->method, row_arg, d->fixed_pivot, d->u0_fixed, d->fixed_target,
+                                         d->index_width > 0 ? d->index_width : 1, d->p0_only, res, sm + L.o_sws, sm + L.o_ph, st));
+    XMR_CU(cudaMemcpyAsync(ctl_pinned, sm + L.o_arg, 256, cudaMemcpyDeviceToHost, st));
+    return XMR_OK;
+}
+
+// per-thread state of the device chain: pinned landing buffer, events, capture stream, a small graph cache
+struct GraphEntry {
+    unsigned char key[160];
+    int seen = 0;
+    cudaGraphExec_t exec = nullptr;
+};
+struct ChainState {
+    unsigned char* ctl_pinned = nullptr;
+    cudaEvent_t t_begin = nullptr, searched = nullptr, t_end = nullptr;
+    cudaStream_t cap = nullptr;
+    int dev = -1;
+    GraphEntry cache[4];
+    int cache_next = 0;
+    bool timed = false;
+};
+thread_local ChainState g_cs;
+
+int chain_state(ChainState** out) {
     int dev = 0;
     XMR_CU(cudaGetDevice(&dev));
-    if (state_dev != dev) {
-        if (ctl_pinned) { cudaFreeHost(ctl_pinned); cudaEventDestroy(searched); cudaStreamDestroy(cap); }
-        for (GraphEntry& e : cache) { if (e.exec) cudaGraphExecDestroy(e.exec); e = GraphEntry(); }
-        XMR_CU(cudaMallocHost(reinterpret_cast<void**>(&ctl_pinned), 256));
-        XMR_CU(cudaEventCreateWithFlags(&searched, cudaEventDisableTiming));
-        XMR_CU(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
-        state_dev = dev;
+    ChainState& s = g_cs;
+    if (s.dev != dev) {
+        if (s.ctl_pinned) {
+            cudaFreeHost(s.ctl_pinned);
+            cudaEventDestroy(s.t_begin);
+            cudaEventDestroy(s.searched);
+            cudaEventDestroy(s.t_end);
+            cudaStreamDestroy(s.cap);
+        }
+        for (GraphEntry& e : s.cache) {
+            if (e.exec) cudaGraphExecDestroy(e.exec);
+            e = GraphEntry();
+        }
+        XMR_CU(cudaMallocHost(reinterpret_cast<void**>(&s.ctl_pinned), 256));
+        XMR_CU(cudaEventCreate(&s.t_begin));
+        XMR_CU(cudaEventCreate(&s.searched));
+        XMR_CU(cudaEventCreate(&s.t_end));
+        XMR_CU(cudaStreamCreateWithFlags(&s.cap, cudaStreamNonBlocking));
+        s.dev = dev;
+        s.timed = false;
     }
+    *out = &s;
+    return XMR_OK;
+}
+
+// pass 2 with the phase parameters in device memory, then wait for the control block (pass 2 keeps running)
+int chain_finish(const xmr_host_chain_desc* d, const void* fid_dev, void* spec_dev, int64_t batch, int window_mode,
+                 const float* window_dev, const float* rows, float scale, unsigned char* sm, ChainState& cs, double* result_host,
+                 cudaStream_t st) {
+    const ChainLayout L(batch, d->n_out);
+    int rc;
+    XMR_CU(cudaEventRecord(cs.searched, st));
+    if (batch > 0)
+        XMR_RC(xmr_abi::k1_dispatch(fid_dev, spec_dev, batch, d->n_in, d->n_out, d->pad_left, window_mode, window_dev, rows, scale, 0, 0,
+                                    d->n_out / 2, nullptr, nullptr, XMR_PHASE_UNIFORM, 0.0, 0.0, nullptr, nullptr, 0, sm + L.o_ph, st));
+    XMR_CU(cudaEventRecord(cs.t_end, st));
+    cs.timed = true;
+    XMR_CU(cudaEventSynchronize(cs.searched));     // the control block has landed; pass 2 keeps running
+    unsigned char ctl[256];
+    std::memcpy(ctl, cs.ctl_pinned, 256);
+    float vmax;
+    long long grow;
+    double res_h[4];
+    int idx;
+    std::memcpy(&vmax, ctl, 4);
+    std::memcpy(&grow, ctl + 16, 8);
+    std::memcpy(res_h, ctl + 64, 32);
+    std::memcpy(&idx, ctl + 144, 4);
+    result_host[0] = res_h[0];
+    result_host[1] = d->p0_only ? 0.0 : res_h[1];
+    result_host[2] = double(d->fixed_pivot ? d->fixed_target : idx);
+    result_host[3] = res_h[2];
+    result_host[4] = double(vmax);
+    result_host[5] = double(grow);
+    return XMR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// {front part ms (pass 1 ... search), pass 2 ms} of this thread's last device chain (waits for its pass 2)
+int xmr_chain_single_last_timing(double* ms_out) {
+    ChainState& cs = g_cs;
+    if (!ms_out) return xmr_abi::fail(XMR_ERR_BAD_ARG, "NULL pointer");
+    if (!cs.timed) return xmr_abi::fail(XMR_ERR_BAD_ARG, "no device chain has run on this thread");
+    float a = 0.f, b = 0.f;
+    XMR_CU(cudaEventSynchronize(cs.t_end));
+    XMR_CU(cudaEventElapsedTime(&a, cs.t_begin, cs.searched));
+    XMR_CU(cudaEventElapsedTime(&b, cs.searched, cs.t_end));
+    ms_out[0] = double(a);
+    ms_out[1] = double(b);
+    return XMR_OK;
+}
+
+int xmr_chain_single_front_c64(const xmr_host_chain_desc* d, const void* fid_dev, int64_t batch, int window_mode,
+                               const float* window_dev, const float* win_rows_host, void* workspace_dev, int64_t row_offset,
+                               void* slot_dev, void* stream) {
+    int rc = check_chain_args(d, batch);
+    if (rc != XMR_OK) return rc;
+    if ((batch > 0 && !fid_dev) || !workspace_dev || !slot_dev) return xmr_abi::fail(XMR_ERR_BAD_ARG, "NULL pointer");
+    ChainState* cs = nullptr;
+    XMR_RC(chain_state(&cs));
+    const float scale = d->scale != 0.f ? d->scale : 1.0f / std::sqrt(float(d->n_out));
+    float ones[32];
+    for (float& r : ones) r = 1.0f;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    XMR_CU(cudaEventRecord(cs->t_begin, st));
+    return chain_front(d, fid_dev, batch, window_mode, window_dev, win_rows_host ? win_rows_host : ones, scale,
+                       static_cast<unsigned char*>(workspace_dev), row_offset, slot_dev, st);
+}
+
+int xmr_chain_single_back_c64(const xmr_host_chain_desc* d, const void* fid_dev, void* spec_dev, int64_t batch, int window_mode,
+                              const float* window_dev, const float* win_rows_host, void* workspace_dev, const void* gathered_dev,
+                              int world, double* result_host, void* stream) {
+    int rc = check_chain_args(d, batch);
+    if (rc != XMR_OK) return rc;
+    if ((batch > 0 && (!fid_dev || !spec_dev)) || !workspace_dev || !gathered_dev || !result_host || world < 1)
+        return xmr_abi::fail(XMR_ERR_BAD_ARG, "NULL pointer / world < 1");
+    ChainState* cs = nullptr;
+    XMR_RC(chain_state(&cs));
+    const float scale = d->scale != 0.f ? d->scale : 1.0f / std::sqrt(float(d->n_out));
+    float ones[32];
+    for (float& r : ones) r = 1.0f;
+    const float* rows = win_rows_host ? win_rows_host : ones;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned char* sm = static_cast<unsigned char*>(workspace_dev);
+    XMR_RC(chain_mid(d, batch, window_mode, window_dev, rows, scale, sm, gathered_dev, world, cs->ctl_pinned, st));
+    return chain_finish(d, fid_dev, spec_dev, batch, window_mode, window_dev, rows, scale, sm, *cs, result_host, st);
+}
+
+int xmr_chain_single_dev_c64(const xmr_host_chain_desc* d, const void* fid_dev, void* spec_dev, int64_t batch, int window_mode,
+                             const float* window_dev, const float* win_rows_host, void* workspace_dev, double* result_host,
+                             void* stream) {
+    int rc = check_chain_args(d, batch);
+    if (rc != XMR_OK) return rc;
+    if (batch == 0) return XMR_OK;
+    if (!fid_dev || !spec_dev || !workspace_dev || !result_host) return xmr_abi::fail(XMR_ERR_BAD_ARG, "NULL pointer");
+    const int n_in = d->n_in, n_out = d->n_out;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned char* sm = static_cast<unsigned char*>(workspace_dev);
+    const ChainLayout L(batch, n_out);
+    const float scale = d->scale != 0.f ? d->scale : 1.0f / std::sqrt(float(n_out));
+    float ones[32];
+    for (float& r : ones) r = 1.0f;
+    const float* rows = win_rows_host ? win_rows_host : ones;
+    ChainState* csp = nullptr;
+    XMR_RC(chain_state(&csp));
+    ChainState& cs = *csp;
+    // Everything between the two passes takes its inputs from device memory: the winning row (candidate slot + winner record),
+    // the pivot (the winner's own argmax) and the phase parameters of pass 2 (written by the search's final kernel).  Nothing is
+    // read back before pass 2 is enqueued.  The ~14 launches up to the search's final kernel (+ the 256-byte control block's
+    // copy to pinned host memory) are captured ONCE per argument set into a CUDA graph and replayed: small batches are
+    // launch-bound otherwise (C2: 4096 x 2048 spends more time between its kernels than in them).
+    auto enqueue_front = [&](cudaStream_t s) -> int {
+        int r = chain_front(d, fid_dev, batch, window_mode, window_dev, rows, scale, sm, 0, sm + L.o_slot, s);
+        if (r != XMR_OK) return r;
+        return chain_mid(d, batch, window_mode, window_dev, rows, scale, sm, sm + L.o_slot, 1, cs.ctl_pinned, s);
+    };
     unsigned char key[160];
     std::memset(key, 0, sizeof(key));
     {
@@ -436,16 +593,16 @@ int xmr_chain_single_dev_c64(const xmr_host_chain_desc* d, const void* fid_dev, 
         put(rsum, 8);
     }
     GraphEntry* ent = nullptr;
-    for (GraphEntry& e : cache)
+    for (GraphEntry& e : cs.cache)
         if (e.seen && std::memcmp(e.key, key, sizeof(key)) == 0) ent = &e;
     bool launched = false;
     if (ent != nullptr && ent->exec == nullptr && ent->seen == 1) {
         // second call with these arguments (tables and kernel attributes exist now): capture
         ent->seen = 2;
         cudaGraph_t graph = nullptr;
-        if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-            const int crc = enqueue_front(cap, ctl_pinned);
-            const cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+        if (cudaStreamBeginCapture(cs.cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int crc = enqueue_front(cs.cap);
+            const cudaError_t ce = cudaStreamEndCapture(cs.cap, &graph);
             if (crc == XMR_OK && ce == cudaSuccess && graph != nullptr) {
                 if (cudaGraphInstantiate(&ent->exec, graph, 0) != cudaSuccess) ent->exec = nullptr;
             }
@@ -453,45 +610,25 @@ int xmr_chain_single_dev_c64(const xmr_host_chain_desc* d, const void* fid_dev, 
         }
         cudaGetLastError();     // a failed capture leaves the eager path below (same kernels, same stream order)
     }
+    XMR_CU(cudaEventRecord(cs.t_begin, st));
     if (ent != nullptr && ent->exec != nullptr) {
         XMR_CU(cudaGraphLaunch(ent->exec, st));
         launched = true;
         ++g_graph_launches;
     }
     if (!launched) {
-        XMR_RC(enqueue_front(st, ctl_pinned));
+        XMR_RC(enqueue_front(st));
         if (ent == nullptr) {
-            GraphEntry& e = cache[cache_next];
-            cache_next = (cache_next + 1) % 4;
+            GraphEntry& e = cs.cache[cs.cache_next];
+            cs.cache_next = (cs.cache_next + 1) % 4;
             if (e.exec) cudaGraphExecDestroy(e.exec);
             e = GraphEntry();
             std::memcpy(e.key, key, sizeof(key));
             e.seen = 1;
         }
     }
-    XMR_CU(cudaEventRecord(searched, st));
-    XMR_RC(xmr_abi::k1_dispatch(fid_dev, spec_dev, batch, n_in, n_out, d->pad_left, window_mode, window_dev, rows, scale, 0, 0, n_out / 2,
-                                nullptr, nullptr, XMR_PHASE_UNIFORM, 0.0, 0.0, nullptr, nullptr, sm + o_ph, st));
-    XMR_CU(cudaEventSynchronize(searched));     // the control block has landed; pass 2 keeps running
-#undef XMR_RC
-    unsigned char ctl[256];
-    std::memcpy(ctl, ctl_pinned, 256);
-    float vmax;
-    long long flat;
-    double res_h[4];
-    int idx;
-    std::memcpy(&vmax, ctl, 4);
-    std::memcpy(&flat, ctl + 8, 8);
-    std::memcpy(res_h, ctl + 64, 32);
-    std::memcpy(&idx, ctl + 144, 4);
-    result_host[0] = res_h[0];
-    result_host[1] = d->p0_only ? 0.0 : res_h[1];
-    result_host[2] = double(d->fixed_pivot ? d->fixed_target : idx);
-    result_host[3] = res_h[2];
-    result_host[4] = double(vmax);
-    result_host[5] = double(flat / n_out);
-    return XMR_OK;
+    return chain_finish(d, fid_dev, spec_dev, batch, window_mode, window_dev, rows, scale, sm, cs, result_host, st);
 }
-
+#undef XMR_RC
 
 }  // extern "C"

@@ -46,8 +46,8 @@ struct K1Params {
     float2 ph_step[16];    // exp(2 pi i * b * R0*R1 * d), d < 16
     float2 ph_fold[16];    // folded-phase variants: exp(2 pi i (a + b * ((R0*R1*d + N/2) mod N))), d < 16
     float* run_max2;       // k1_max_kernel: running global max of |S|^2 (device scalar, zeroed by the launcher)
-    const long long* row_flat;   // generic kernel, optional: transform row (*row_flat / row_div) of `in` (device-resident winner)
-    int row_div;
+    const long long* row_slot;   // generic kernel, optional: transform the row starting at in + (*row_slot) * row_stride
+    int row_stride;              //   (the device-resident winner among the gathered candidate rows; elements)
     const K1PhaseDev* ph_dev;    // optional: phase parameters from device memory instead of ph_* above
 };
 
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
     constexpr bool PHDEV = F && ((FAST & K1_FAST_PHDEV) != 0);
     constexpr bool PH_TABLE = !F || PHDEV;          // the epilogue reads its step / fold phasors from shared memory
     const float2* in_base = p.in;
-    if (!F && p.row_flat != nullptr) in_base += (*p.row_flat / p.row_div) * (long long)p.n_in;
+    if (!F && p.row_slot != nullptr) in_base += (*p.row_slot) * (long long)p.row_stride;
     double ph_a_turns = p.ph_a_turns, ph_b_turns = p.ph_b_turns;
     if (PH_TABLE) {
         if (p.ph_dev != nullptr) {

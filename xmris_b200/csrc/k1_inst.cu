@@ -91,7 +91,7 @@ cudaError_t XMR_CAT(k1_launch_, XMR_N)(const K1Params& p, bool inverse, int win,
         return tma ? launch_one<XMR_N, true, 2, true>(p, max_ctas, st) : launch_one<XMR_N, true, 2, false>(p, max_ctas, st);
     }
     // hot path: full-length input, separable window, TMA, fftshift store -> compile-time epilogue variants
-    const bool fast_geom = p.row_flat == nullptr && tma && win == 2 && p.n_in == XMR_N && p.pad_left == 0 && p.in_shift == 0 &&
+    const bool fast_geom = p.row_slot == nullptr && tma && win == 2 && p.n_in == XMR_N && p.pad_left == 0 && p.in_shift == 0 &&
                            p.out_shift == XMR_N / 2 && XMR_N >= 512;
     if (fast_geom) {
         const bool st_ = p.out != nullptr, stats = p.absmax != nullptr && p.argmax == nullptr, ph = p.phase_on != 0;

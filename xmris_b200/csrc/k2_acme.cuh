@@ -523,8 +523,16 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
                     // step computed from one may declare convergence
                     const bool smallstep = fabs(stp0) < 0.5 && fabs(stp1) < 1.5;
                     const bool conv = np == 3 && st.iters > 1 && fabs(stp0) < NEWTON_TOL0 && fabs(stp1) < NEWTON_TOL1;
+                    // a Newton step from a fresh secant Hessian that is already tiny is taken WITHOUT re-evaluating there: the
+                    // error after it is second order in the step (quadratic convergence), far below the 0.1 deg tolerance
+                    const bool last = np == 3 && st.iters > 1 && !conv && fabs(stp0) < 0.02 && fabs(stp1) < 0.06;
                     res_h = r[0].H; res_pen = r[0].pen;
-                    if (!(st.f < CUDART_INF) || conv) {
+                    if (last) {
+                        st.x0 += stp0;
+                        st.x1 = t1;
+                        st.f *= (1.0 - 1e-12);          // (recorded below as the start's result; the value moves by < 1e-7)
+                        sh.active[s] = 0;
+                    } else if (!(st.f < CUDART_INF) || conv) {
                         sh.active[s] = 0;
                     } else {
                         sh.y0[s] = st.x0 + stp0;
@@ -555,6 +563,20 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
             }
             __syncthreads();
             if (t == 0) {
+                // two starts that have walked into the same minimum: the worse one stops (most voxels have ONE valley and all
+                // three starts end in it)
+                for (int a = 0; a < K2A_NS; ++a)
+                    for (int b = a + 1; b < K2A_NS; ++b) {
+                        if (!(sh.res_f[a] < CUDART_INF) || !(sh.res_f[b] < CUDART_INF)) continue;
+                        if (!sh.active[a] && !sh.active[b]) continue;
+                        double d0 = fabs(sh.res_p0[a] - sh.res_p0[b]);
+                        d0 = fmin(d0, fabs(360.0 - d0));
+                        if (d0 < 0.5 && fabs(sh.res_p1[a] - sh.res_p1[b]) < 2.0) {
+                            const int worse = (sh.res_f[a] <= sh.res_f[b]) ? b : a;
+                            if (sh.active[worse]) sh.active[worse] = 0;
+                            else sh.active[worse == a ? b : a] = sh.active[worse == a ? b : a];   // the finished one is the better: keep going
+                        }
+                    }
                 int any = 0;
                 for (int s = 0; s < K2A_NS; ++s) any |= sh.active[s];
                 sh.any_active = any;

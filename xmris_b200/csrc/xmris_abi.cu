@@ -171,6 +171,37 @@ __global__ void global_argmax_kernel(const float* __restrict__ absmax, const int
     }
 }
 
+// ---- multi-GPU exchange of mode="single" without the host (sharding.py): every rank packs its best row + record, ONE
+// all-gather moves them, every rank selects the global winner on the device and searches it redundantly ----------------------
+// slot layout (complex64 elements, slot_elems = even(n_in) + 2): [0, n_in) the FID row | element slot_elems-2: {float max |S|, 0}
+// | element slot_elems-1: int64 global row
+__global__ void pack_winner_kernel(const float2* __restrict__ fid, long long batch, int n_in, int n_out, int slot_elems,
+                                   const unsigned char* __restrict__ arg_record, long long row_offset, float2* __restrict__ slot) {
+    const float vmax = batch > 0 ? *reinterpret_cast<const float*>(arg_record) : -1.f;
+    const long long row = batch > 0 ? *reinterpret_cast<const long long*>(arg_record + 8) / n_out : 0;
+    for (int k = threadIdx.x; k < n_in; k += blockDim.x) slot[k] = batch > 0 ? fid[row * n_in + k] : make_float2(0.f, 0.f);
+    if (threadIdx.x == 0) {
+        slot[slot_elems - 2] = make_float2(vmax, 0.f);
+        *reinterpret_cast<long long*>(slot + slot_elems - 1) = batch > 0 ? row + row_offset : 0x7fffffffffffffffLL;
+    }
+}
+// ctl: {float max @0, int64 winning slot @8, int64 global row @16}; ties go to the lowest global row (numpy argmax order)
+__global__ void select_winner_kernel(const float2* __restrict__ gathered, int world, int slot_elems, unsigned char* ctl) {
+    if (threadIdx.x == 0) {
+        float best = -2.f;
+        long long brow = 0x7fffffffffffffffLL, bslot = 0;
+        for (int r = 0; r < world; ++r) {
+            const float2* s = gathered + (long long)r * slot_elems;
+            const float v = s[slot_elems - 2].x;
+            const long long row = *reinterpret_cast<const long long*>(s + slot_elems - 1);
+            if (v > best || (v == best && row < brow)) { best = v; brow = row; bslot = r; }
+        }
+        *reinterpret_cast<float*>(ctl) = best;
+        *reinterpret_cast<long long*>(ctl + 8) = bslot;
+        *reinterpret_cast<long long*>(ctl + 16) = brow;
+    }
+}
+
 int grid_for(long long total, int block) {
     long long g = (total + block - 1) / block;
     const long long cap = 148LL * 16;
@@ -187,13 +218,13 @@ const char* xmr_last_error(void) { return xmr_abi::g_err; }
 }  // extern "C"
 
 namespace xmr_abi {
-// row_flat_dev (optional): transform row (*row_flat_dev / n_out) of fid_dev (batch must be 1);
+// row_slot_dev (optional): transform the row at fid_dev + (*row_slot_dev) * row_stride elements (batch must be 1);
 // ph_dev (optional, phase_mode = XMR_PHASE_UNIFORM): xmr::K1PhaseDev in device memory instead of ph_a_turns / ph_b_turns
 int k1_dispatch(const void* fid_dev, void* spec_dev, int64_t batch, int n_in, int n_out, int pad_left,
                 int window_mode, const float* window_dev, const float* win_rows_host, float scale,
                 int inverse, int in_shift, int out_shift, float* absmax_dev, int* argmax_dev,
-                int phase_mode, double ph_a_turns, double ph_b_turns, float* run_max2, const long long* row_flat_dev,
-                const void* ph_dev, void* stream) {
+                int phase_mode, double ph_a_turns, double ph_b_turns, float* run_max2, const long long* row_slot_dev,
+                int row_stride, const void* ph_dev, void* stream) {
     if (!supported_n(n_out))
         return fail(XMR_ERR_UNSUPPORTED_N, "n_out=%d: transform length must be a power of two in [16, 8192]", n_out);
     if (batch < 0 || n_in < 1 || n_in > n_out || pad_left < 0 || pad_left + n_in > n_out)
@@ -236,10 +267,10 @@ int k1_dispatch(const void* fid_dev, void* spec_dev, int64_t batch, int n_in, in
     p.absmax = absmax_dev;
     p.argmax = argmax_dev;
     p.run_max2 = run_max2;
-    p.row_flat = row_flat_dev;
-    p.row_div = n_out;
+    p.row_slot = row_slot_dev;
+    p.row_stride = row_stride;
     p.ph_dev = static_cast<const xmr::K1PhaseDev*>(ph_dev);
-    if (row_flat_dev != nullptr && batch != 1) return fail(XMR_ERR_BAD_ARG, "row_flat_dev needs batch == 1");
+    if (row_slot_dev != nullptr && (batch != 1 || (row_stride & 1))) return fail(XMR_ERR_BAD_ARG, "row_slot_dev needs batch == 1 and an even stride");
     const int r0 = n_out >= 256 ? n_out / 256 : 1;
     for (int i = 0; i < 32; ++i) p.win_rows[i] = 1.0f;
     int win = 2;
@@ -281,6 +312,24 @@ int k1_dispatch(const void* fid_dev, void* spec_dev, int64_t batch, int n_in, in
 }
 }  // namespace xmr_abi
 
+namespace xmr_abi {
+int pack_winner(const void* fid_dev, int64_t batch, int n_in, int n_out, const void* arg_record_dev, int64_t row_offset,
+                void* slot_dev, void* stream) {
+    pack_winner_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float2*>(fid_dev), batch, n_in, n_out,
+                                                                        ((n_in + 1) & ~1) + 2,
+                                                                        static_cast<const unsigned char*>(arg_record_dev), row_offset,
+                                                                        static_cast<float2*>(slot_dev));
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? XMR_OK : cuda_fail(e, "pack_winner launch");
+}
+int select_winner(const void* gathered_dev, int world, int n_in, void* ctl_dev, void* stream) {
+    select_winner_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float2*>(gathered_dev), world, ((n_in + 1) & ~1) + 2,
+                                                                         static_cast<unsigned char*>(ctl_dev));
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? XMR_OK : cuda_fail(e, "select_winner launch");
+}
+}  // namespace xmr_abi
+
 extern "C" {
 using xmr_abi::k1_dispatch;
 
@@ -289,7 +338,7 @@ int xmr_fid_to_spectrum_c64(const void* fid_dev, void* spec_dev, int64_t batch, 
                             int inverse, int in_shift, int out_shift, float* absmax_dev, int* argmax_dev,
                             int phase_mode, double ph_a_turns, double ph_b_turns, void* stream) {
     return k1_dispatch(fid_dev, spec_dev, batch, n_in, n_out, pad_left, window_mode, window_dev, win_rows_host, scale, inverse,
-                       in_shift, out_shift, absmax_dev, argmax_dev, phase_mode, ph_a_turns, ph_b_turns, nullptr, nullptr, nullptr, stream);
+                       in_shift, out_shift, absmax_dev, argmax_dev, phase_mode, ph_a_turns, ph_b_turns, nullptr, nullptr, 0, nullptr, stream);
 }
 
 int xmr_fid_absmax_pruned_c64(const void* fid_dev, int64_t batch, int n_in, int n_out, int pad_left, int window_mode,
@@ -301,7 +350,7 @@ int xmr_fid_absmax_pruned_c64(const void* fid_dev, int64_t batch, int n_in, int 
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(running max)");
     }
     return k1_dispatch(fid_dev, nullptr, batch, n_in, n_out, pad_left, window_mode, window_dev, win_rows_host, scale, 0, 0,
-                       n_out / 2, absmax_dev, nullptr, XMR_PHASE_NONE, 0.0, 0.0, running_max2_dev, nullptr, nullptr, stream);
+                       n_out / 2, absmax_dev, nullptr, XMR_PHASE_NONE, 0.0, 0.0, running_max2_dev, nullptr, 0, nullptr, stream);
 }
 
 int xmr_zero_fill_c64(const void* in_dev, void* out_dev, int64_t batch, int n_in, int n_out, int pad_left,

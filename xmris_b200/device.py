@@ -431,13 +431,21 @@ def baseline_als(x, lam=1e5, p=0.001, n_iter=10, out=None, stream=None):
 _chain_workspaces: dict = {}
 
 
+_exchange_buffers: dict = {}
+
+
 def chain_single_dev(fid, n_out, pad_left, window, du, method="acme", index_width=1, p0_only=False, fixed=None, out=None,
-                     stream=None):
+                     stream=None, all_gather=None, row_offset=0):
     """``mode="single"`` chain on a device-resident ``[batch, n_in]`` tensor through ONE C-ABI call
-    (``xmr_chain_single_dev_c64``: pass 1, argmax, winning spectrum, search, pass 2 -- no Python between the launches).
+    (``xmr_chain_single_dev_c64``: pass 1, argmax, winning spectrum, search, pass 2 -- no Python between the launches,
+    no host read-back between the passes, the front part replayed as a CUDA graph).
 
     ``window``: a :class:`PreparedWindow` or None; ``fixed``: ``None`` or ``(u0, target_idx)`` when ``target_coord`` is
-    given.  Returns ``(spectrum, result)`` with ``result = [p0, p1, pivot index, fun, max |S|, winning row]`` (host)."""
+    given.  ``all_gather`` (multi-GPU, voxels sharded over ranks): a callable ``(recv [world, slot] uint8, send [slot]
+    uint8) -> None`` that all-gathers the ranks' candidate slots on the current stream (``torch.distributed``); the chain
+    then runs as ``xmr_chain_single_front_c64`` -> that ONE collective -> ``xmr_chain_single_back_c64`` and every rank
+    searches the global winner redundantly; ``row_offset`` = first global row of this rank's shard.
+    Returns ``(spectrum, result)`` with ``result = [p0, p1, pivot index, fun, max |S|, winning (global) row]`` (host)."""
     torch = _torch()
     lib = _lib.load()
     _require_cuda(fid, "fid")
@@ -477,10 +485,35 @@ def chain_single_dev(fid, n_out, pad_left, window, du, method="acme", index_widt
         _chain_workspaces[key] = ws
     result = (ctypes.c_double * 6)()
     with torch.cuda.device(dev):
-        _lib.check(lib.xmr_chain_single_dev_c64(ctypes.byref(desc), _ptr(fid), _ptr(out), batch, win_mode, _ptr(win_dev),
-                                                ctypes.cast(rows_arr, ctypes.c_void_p), _ptr(ws),
-                                                ctypes.cast(result, ctypes.c_void_p), _stream_ptr(stream)))
+        if all_gather is None:
+            _lib.check(lib.xmr_chain_single_dev_c64(ctypes.byref(desc), _ptr(fid), _ptr(out), batch, win_mode, _ptr(win_dev),
+                                                    ctypes.cast(rows_arr, ctypes.c_void_p), _ptr(ws),
+                                                    ctypes.cast(result, ctypes.c_void_p), _stream_ptr(stream)))
+        else:
+            world = int(all_gather.world_size)
+            slot_bytes = int(lib.xmr_chain_single_slot_bytes(int(n_in)))
+            bkey = key + (slot_bytes, world)
+            bufs = _exchange_buffers.get(bkey)
+            if bufs is None:
+                bufs = (torch.zeros(slot_bytes, dtype=torch.uint8, device=dev),
+                        torch.zeros((world, slot_bytes), dtype=torch.uint8, device=dev))
+                _exchange_buffers[bkey] = bufs
+            send, recv = bufs
+            _lib.check(lib.xmr_chain_single_front_c64(ctypes.byref(desc), _ptr(fid), batch, win_mode, _ptr(win_dev),
+                                                      ctypes.cast(rows_arr, ctypes.c_void_p), _ptr(ws), int(row_offset),
+                                                      _ptr(send), _stream_ptr(stream)))
+            all_gather(recv, send)                       # the ONE collective of the chain
+            _lib.check(lib.xmr_chain_single_back_c64(ctypes.byref(desc), _ptr(fid), _ptr(out), batch, win_mode, _ptr(win_dev),
+                                                     ctypes.cast(rows_arr, ctypes.c_void_p), _ptr(ws), _ptr(recv), world,
+                                                     ctypes.cast(result, ctypes.c_void_p), _stream_ptr(stream)))
     return out, [float(v) for v in result]
+
+
+def chain_single_last_timing():
+    """``(front ms, pass 2 ms)`` of the calling thread's last device chain (CUDA events on its stream; waits for pass 2)."""
+    ms = (ctypes.c_double * 2)()
+    _lib.check(_lib.load().xmr_chain_single_last_timing(ctypes.cast(ms, ctypes.c_void_p)))
+    return float(ms[0]), float(ms[1])
 
 
 def autophase_search(spec1d, u0, du, method="acme", target_idx=0, index_width=1, p0_only=False, stream=None):

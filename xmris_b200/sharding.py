@@ -39,6 +39,50 @@ def pick_winner(values, flat_indices, row_offsets):
     return best, int(flat_indices[best]) + int(row_offsets[best])
 
 
+def slot_elems(n_in: int) -> int:
+    """complex64 elements of one candidate slot: the FID row (padded to an even length), then {max |S|, 0}, then the int64
+    global row (``pack_winner_kernel`` / ``select_winner_kernel`` in ``csrc/xmris_abi.cu``)."""
+    return ((n_in + 1) & ~1) + 2
+
+
+def pack_slot(row_fid, vmax, global_row):
+    """Host mirror of ``pack_winner_kernel`` (tests and documentation of the wire layout): one slot as complex64."""
+    n_in = len(row_fid)
+    slot = np.zeros(slot_elems(n_in), dtype=np.complex64)
+    slot[:n_in] = row_fid
+    slot[-2] = np.float32(vmax)
+    slot[-1:].view(np.int64)[0] = global_row
+    return slot
+
+
+def select_winner(gathered):
+    """Host mirror of ``select_winner_kernel``: ``(slot index, max |S|, global row)`` of the winner among ``[world, slot]``
+    gathered slots; ties go to the lowest global row (numpy ``argmax`` order over the concatenated shards)."""
+    best, brow, bslot = -2.0, np.iinfo(np.int64).max, 0
+    for r in range(gathered.shape[0]):
+        v = float(gathered[r, -2].real)
+        row = int(gathered[r, -1:].view(np.int64)[0])
+        if v > best or (v == best and row < brow):
+            best, brow, bslot = v, row, r
+    return bslot, best, brow
+
+
+class SlotAllGather:
+    """The ONE collective of the sharded ``mode="single"`` chain: all-gather of the ranks' candidate slots
+    (``xmr_chain_single_front_c64`` -> this -> ``xmr_chain_single_back_c64``, see ``device.chain_single_dev``).
+
+    Enqueued on the current CUDA stream by ``torch.distributed`` (NCCL): no host synchronisation, no second collective --
+    every rank selects the winner on the device and runs the 0.3 ms search redundantly instead of waiting for a broadcast.
+    """
+
+    def __init__(self, dist, group=None):
+        self.dist, self.group = dist, group
+        self.world_size = dist.get_world_size(group)
+
+    def __call__(self, recv, send):
+        self.dist.all_gather_into_tensor(recv.view(-1), send, group=self.group)
+
+
 def make_exchange(dist, device, n_out: int, row_offset_elems: int):
     """Build the ``exchange`` callable for :func:`xmris_b200.chain.chain_single` on an initialised process group.
 
