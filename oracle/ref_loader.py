@@ -2,9 +2,8 @@
 
 Only usable where ``/root/reference`` exists (the build container); it does not travel to the GPU
 box, so nothing under ``-m gpu``, ``smoke()`` or ``bench.py`` may depend on it.  It is used by
-``tests/golden/make_golden.py`` to generate the committed golden vectors and by
-``tests/test_oracle_vs_reference.py`` (skipped when the reference tree is absent) to pin
-``oracle/xmris_oracle.py`` against the real reference code.
+``tests/golden/make_golden*.py`` to generate the committed golden vectors (outputs of the reference's
+own code), which ``tests/test_oracle.py`` then uses to pin ``oracle/xmris_oracle.py`` bit-exactly.
 
 How (strategy 2): ``import xmris`` cannot work here (its ``__init__`` pulls
 matplotlib / pyAMARES, and xarray itself is not installed).  We therefore

@@ -43,7 +43,7 @@ struct K2aSmem {
     static constexpr size_t B = (C::SIZE_B > SPN ? size_t(C::SIZE_B) : SPN) * sizeof(float2);
     static constexpr size_t DEC = size_t(K2A_NDEC) * (sizeof(float2) + sizeof(float));
     static constexpr size_t ROWS = size_t(192) * 2 * sizeof(float);
-    static constexpr size_t MISC = 4096;
+    static constexpr size_t MISC = 8192;
     static constexpr size_t TOTAL = SLOT + B + DEC + ROWS + MISC;
 };
 
@@ -53,7 +53,8 @@ struct K2aShared {      // lives in the MISC area
     int redi[32];
     float cell_p0[K2A_T], cell_p1[K2A_T];
     float l2f[K2A_T * 3], l2p0[K2A_T * 3], l2p1[K2A_T * 3];
-    double part[K2A_NS][2][3][GRAD_NSUMS];    // [start][segment][evaluation point][sum]
+    float part[K2A_NS][8][3][GRAD_NSUMS];     // [start][segment][evaluation point][sum] (per-warp float32 partial sums)
+    int gs;                                   // segments (warps) per active start in this iteration
     double y0[K2A_NS], y1[K2A_NS];            // trial point per start
     int np[K2A_NS];                           // evaluation points wanted at the trial point: 1 (gradient) or 3 (+ secant Hessian)
     int active[K2A_NS];
@@ -65,7 +66,7 @@ struct K2aShared {      // lives in the MISC area
     float zc0, zc1, zcf;
     int wall;
 };
-static_assert(sizeof(K2aShared) <= 4096, "K2aShared must fit the MISC area");
+static_assert(sizeof(K2aShared) <= 8192, "K2aShared must fit the MISC area");
 
 template <int N>
 __global__ void __launch_bounds__(FftCfg<N>::T, (N >= 8192 ? 1 : (FftCfg<N>::T >= 256 ? 2 : (FftCfg<N>::T >= 128 ? 4 : 8))))
@@ -76,7 +77,7 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
     constexpr int WPS = C::T / 32;
     constexpr int PADSHIFT = SM::PADSHIFT;
     constexpr int L = N / 32;                      // points per lane when one warp walks the whole spectrum
-    constexpr int GS = (WPS >= 6) ? 2 : 1;         // warps per Newton start
+    constexpr int GSMAX = WPS;                     // warps per Newton start: all of them once a single start is left
     constexpr int DEC = N / K2A_NDEC;
     static_assert(C::T >= 32 && N >= 512, "per-voxel kernel needs N >= 512");
 
@@ -356,13 +357,17 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
         __syncthreads();
 
         // ---- E: L2, the true objective around the K2A_T cells (full spectrum, 3 p1 rows x 8 p0 per cell) ----------------
-        const int l2rows = p.p0_only ? 1 : 3;
-        for (int item = warp; item < K2A_T * l2rows; item += WPS) {
-            const int cell = item / l2rows, rr = item - cell * l2rows;
+        // 3 rows (cell.p1 - 15, 0, + 15) for the four best cells, 2 rows (-+ 7.5) for the other two: 16 walks = two full rounds
+        // of 8 warps
+        const int l2items = p.p0_only ? K2A_T : 16;
+        for (int item = warp; item < l2items; item += WPS) {
+            const int cell = p.p0_only ? item : (item < 12 ? item / 3 : 4 + (item - 12) / 2);
+            const int rr = p.p0_only ? 0 : (item < 12 ? item % 3 : (item - 12) % 2);
+            const float dp1 = p.p0_only ? 0.f : (item < 12 ? K2A_L2_DP1 * float(rr - 1) : K2A_L2_DP1 * (float(rr) - 0.5f));
             const float c0c = sh.cell_p0[cell], c1c = sh.cell_p1[cell];
             float rbf = CUDART_INF_F, rb0 = 0.f, rb1 = 0.f;
             if (c0c == c0c) {                                       // (warp-uniform)
-                const float p1 = p.p0_only ? 0.f : fminf(fmaxf(c1c + K2A_L2_DP1 * float(rr - 1), -4000.f), 4000.f);
+                const float p1 = p.p0_only ? 0.f : fminf(fmaxf(c1c + dp1, -4000.f), 4000.f);
                 const float tpu = p1 * (1.0f / 360.0f);
                 float c0[K2_K], s0[K2_K], p0k[K2_K];
 #pragma unroll
@@ -389,7 +394,7 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
         if (t == 0) {
             // the K2A_NS best row results that are mutually distinct (a valley can hold two minima ~20 deg of p1 apart where
             // two branches of max(d) meet: rows of the same cell may both become starts)
-            const int nitems = K2A_T * l2rows;
+            const int nitems = l2items;
             int any = 0;
             for (int s = 0; s < K2A_NS; ++s) {
                 int b = -1;
@@ -415,6 +420,11 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
                 if (ok) sh.l2f[b] = CUDART_INF_F;
             }
             sh.any_active = any;
+            {
+                int nact = 0;
+                for (int s = 0; s < K2A_NS; ++s) nact += sh.active[s];
+                sh.gs = nact <= 1 ? GSMAX : (nact == 2 ? (GSMAX >= 2 ? GSMAX / 2 : 1) : (GSMAX >= 4 ? GSMAX / 4 : 1));
+            }
             sh.l2_f = sh.res_f[0];          // the best sampled point: where the direct search starts if the optimum is a wall
             sh.l2_p0 = sh.res_p0[0];
             sh.l2_p1 = sh.res_p1[0];
@@ -431,9 +441,19 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
         double res_h = 1.0, res_pen = 0.0;
         const double p1_lo = p.p0_only ? 0.0 : -4000.0, p1_hi = p.p0_only ? 0.0 : 4000.0;
         for (int nit = 0; nit < K2A_MAXIT && sh.any_active; ++nit) {
-            for (int slotid = warp; slotid < K2A_NS * GS; slotid += WPS) {
-                const int s = slotid / GS, g = slotid - s * GS;
-                if (!sh.active[s]) continue;
+            // the warps are shared out among the ACTIVE starts: 8 warps -> 2 per start while three run, 4 while two, all 8 for
+            // the last one (most voxels: the starts merge after two or three iterations)
+            const int GS = sh.gs;
+            int act[K2A_NS], nact = 0;
+#pragma unroll
+            for (int s = 0; s < K2A_NS; ++s)
+                if (sh.active[s]) act[nact++] = s;
+            for (int slotid = warp; slotid < nact * GS; slotid += WPS) {
+                const int ai = slotid / GS, g = slotid - ai * GS;
+                int s = act[0];
+#pragma unroll
+                for (int q = 1; q < K2A_NS; ++q)
+                    if (q == ai) s = act[q];
                 // lane chunk: the lane's L points split between the GS warps of this start (keeps the padded layout
                 // conflict-free: lanes stay L points apart)
                 const int m0 = lane * L + g * (L / GS), m1 = m0 + L / GS;
@@ -452,7 +472,11 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
                     a.Al1 += float(um0) * a.Al0;
                     a.umax += float(um0);
                     a.warp_reduce();
-                    if (lane == 0) grad_store(a, sh.part[s][g][k]);
+                    if (lane == 0) {
+                        float* o = sh.part[s][g][k];
+                        o[0] = a.P; o[1] = a.gP0; o[2] = a.gP1; o[3] = a.G2; o[4] = a.T2; o[5] = a.As0; o[6] = a.As1; o[7] = a.Al0;
+                        o[8] = a.Al1; o[9] = a.dmax; o[10] = a.qmax; o[11] = a.umax;
+                    }
                 }
             }
             __syncthreads();
@@ -461,8 +485,15 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
                 const int np = sh.np[s];
                 FG r[3];
                 for (int k = 0; k < np; ++k) {
-                    GradSums<double> tot = grad_load(sh.part[s][0][k]);
-                    if (GS > 1) tot.merge(grad_load(sh.part[s][GS - 1][k]));
+                    GradSums<double> tot;
+                    tot.init();
+                    for (int g = 0; g < sh.gs; ++g) {
+                        const float* o = sh.part[s][g][k];
+                        GradSums<double> pg;
+                        pg.P = o[0]; pg.gP0 = o[1]; pg.gP1 = o[2]; pg.G2 = o[3]; pg.T2 = o[4]; pg.As0 = o[5]; pg.As1 = o[6];
+                        pg.Al0 = o[7]; pg.Al1 = o[8]; pg.dmax = o[9]; pg.qmax = o[10]; pg.umax = o[11];
+                        tot.merge(pg);
+                    }
                     r[k] = acme_finish(tot, N);
                 }
                 const double y0 = sh.y0[s], y1 = sh.y1[s];
@@ -577,9 +608,10 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
                             else sh.active[worse == a ? b : a] = sh.active[worse == a ? b : a];   // the finished one is the better: keep going
                         }
                     }
-                int any = 0;
-                for (int s = 0; s < K2A_NS; ++s) any |= sh.active[s];
+                int any = 0, nact = 0;
+                for (int s = 0; s < K2A_NS; ++s) { any |= sh.active[s]; nact += sh.active[s]; }
                 sh.any_active = any;
+                sh.gs = nact <= 1 ? GSMAX : (nact == 2 ? (GSMAX >= 2 ? GSMAX / 2 : 1) : (GSMAX >= 4 ? GSMAX / 4 : 1));
             }
             __syncthreads();
         }

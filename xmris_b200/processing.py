@@ -142,7 +142,21 @@ def zero_fill(da, dim: str = DIMS.time, target_points: int = 1024, position: str
     var = _zero_filled_coord(da, dim, target_points, position, pad_left)
     if var is not None:
         coords[dim] = var
-    res = xr.DataArray(_from_device(out, axis), dims=da.dims, coords=coords, attrs=dict(da.attrs), name=da.name)
+    # non-index coordinates that run along `dim`: DataArray.pad pads them with NaN (fid.py:251)
+    right = int(target_points) - current - pad_left
+    for k in da.coords:
+        c = da.coords[k]
+        if k == dim or dim not in c.dims:
+            continue
+        widths = [(pad_left, right) if d == dim else (0, 0) for d in c.dims]
+        vals = np.asarray(c.values)
+        vals = vals.astype(float) if vals.dtype.kind in "iub" else vals
+        fill = np.nan if vals.dtype.kind in "fc" else None
+        coords[k] = xr.Variable(c.dims, np.pad(vals, widths, mode="constant", constant_values=fill), attrs=dict(c.attrs))
+    values = _from_device(out, axis)
+    if not np.iscomplexobj(np.asarray(da.values)):
+        values = values.real.astype(np.asarray(da.values).dtype, copy=False)      # real data stay real (the reference keeps the dtype)
+    res = xr.DataArray(values, dims=da.dims, coords=coords, attrs=dict(da.attrs), name=da.name)
     res.attrs[ATTRS.zero_fill_target] = target_points
     res.attrs[ATTRS.zero_fill_position] = position
     return res
