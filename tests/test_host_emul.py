@@ -17,7 +17,7 @@ CSRC = os.path.join(ROOT, "xmris_b200", "csrc")
 @pytest.fixture(scope="module")
 def emul():
     path = os.path.join(CSRC, "libxmris_emul.so")
-    src = [os.path.join(CSRC, f) for f in ("host_emul.cpp", "fft_stages.cuh", "fft_regs.cuh", "fft_split.cuh")]
+    src = [os.path.join(CSRC, f) for f in ("host_emul.cpp", "fft_stages.cuh", "fft_regs.cuh")]
     if not os.path.isfile(path) or os.path.getmtime(path) < max(os.path.getmtime(s) for s in src):
         subprocess.run(["make", "-C", CSRC, "emul"], check=True, capture_output=True)
     lib = ctypes.CDLL(path)
@@ -98,32 +98,3 @@ def test_zero_filled_fast_variant_choreography(emul, n_out, zf, persist):
     tw = np.exp(-2j * np.pi * np.arange(n_out) / n_out).astype(np.complex64)
     assert f(x.ctypes.data, out.ctypes.data, 3, n_out, zf, w.ctypes.data, 1.0 / np.sqrt(n_out), tw.ctypes.data, persist) == 0
     assert rel_l2(out, ref) < 5e-7
-
-
-@pytest.mark.parametrize("zf", [1, 2, 4])
-def test_split_8192_even_odd_groups(zf):
-    """N = 8192 as two interleaved 4096-point transforms on two thread groups (csrc/fft_split.cuh, kernel k1_split.cuh):
-    strided in-place exchange A, E / W O exchange, separable window of the 8192-point layout, zero-filled input."""
-    path = os.path.join(CSRC, "libxmris_emul.so")
-    src = [os.path.join(CSRC, f) for f in ("host_emul.cpp", "fft_stages.cuh", "fft_regs.cuh", "fft_split.cuh")]
-    if not os.path.isfile(path) or os.path.getmtime(path) < max(os.path.getmtime(s) for s in src):
-        subprocess.run(["make", "-C", CSRC, "emul"], check=True, capture_output=True)
-    lib = ctypes.CDLL(path)
-    f = lib.xmr_emul_fft_split_c64
-    vp, i = ctypes.c_void_p, ctypes.c_int
-    f.argtypes = [vp, vp, ctypes.c_longlong, i, i, vp, vp, vp, vp]
-    f.restype = i
-    n_out, n_in = 8192, 8192 // zf
-    rng = np.random.default_rng(80 + zf)
-    x = (rng.standard_normal((2, n_in)) + 1j * rng.standard_normal((2, n_in))).astype(np.complex64)
-    t = np.arange(n_in) * 2e-4
-    ref, _ = orc.chain_to_spectrum(x.astype(np.complex128), 1, t, n_out if zf > 1 else None, "end", 5.0)
-    tpad = np.arange(n_out) * 2e-4
-    w = np.exp(-np.pi * 5.0 * tpad) / np.sqrt(n_out)
-    cols = np.ascontiguousarray(w[:256], dtype=np.float32)
-    rows = np.ascontiguousarray(w[::256] / w[0], dtype=np.float32)           # 32 row factors
-    tw_h = np.exp(-2j * np.pi * np.arange(4096) / 4096).astype(np.complex64)
-    tw_n = np.exp(-2j * np.pi * np.arange(8192) / 8192).astype(np.complex64)
-    out = np.zeros((2, n_out), np.complex64)
-    assert f(x.ctypes.data, out.ctypes.data, 2, n_out, zf, cols.ctypes.data, rows.ctypes.data, tw_h.ctypes.data, tw_n.ctypes.data) == 0
-    assert rel_l2(out, ref) < 1e-6

@@ -9,7 +9,6 @@
 #include <cstring>
 #include <vector>
 
-#include "fft_split.cuh"
 #include "fft_stages.cuh"
 
 using namespace xmr;
@@ -99,76 +98,6 @@ extern "C" int xmr_emul_fft_zf_c64(const float* in, float* out, long long batch,
         XMR_CASE(1024, 4) XMR_CASE(2048, 4) XMR_CASE(4096, 4) XMR_CASE(8192, 4)
 #undef XMR_CASE
         return 2;
-    }
-    return 0;
-}
-
-// The even/odd split of N = 2*NH (fft_split.cuh, kernel k1_split.cuh): two thread groups, in-place strided exchange A,
-// E / W O exchange, fftshift store.  Separable window w[256*n1 + n2] = cols[n2] * rows[n1] as the kernel receives it.
-template <int NH, int ZF>
-static void emul_split(const float2* in, float2* out, const float* cols, const float* rows, const float2* twNH, const float2* twN) {
-    using C = FftCfg<NH>;
-    constexpr int N = 2 * NH;
-    static_assert(C::C0 == 1 && C::C2 == 1, "split emulation written for 16 points per thread");
-    std::vector<float2> slot(N, make_float2(0.f, 0.f));
-    std::memcpy(slot.data(), in, sizeof(float2) * (N / ZF));
-    std::vector<float2> B(size_t(2) * C::SIZE_B), XB(size_t(2) * NH);
-    std::vector<float2> regs(size_t(2) * C::T * C::E);
-    std::vector<float2> twp(size_t(C::T) * (C::R0 - 1)), tw0(size_t(C::T) * 2), tw1(size_t(C::T) * C::C1 * 2);
-    for (int t = 0; t < C::T; ++t) init_twiddles<C, false>(t, twNH, &twp[size_t(t) * (C::R0 - 1)], &tw0[size_t(t) * 2], &tw1[size_t(t) * C::C1 * 2]);
-    // stage 0 (every thread reads and rewrites only its own column of its own group: no barrier between load and write)
-    for (int g = 0; g < 2; ++g)
-        for (int t = 0; t < C::T; ++t) {
-            float2* v = &regs[(size_t(g) * C::T + t) * C::E];
-            int n2p, carry;
-            split_window_index<C>(t, 0, g, &n2p, &carry);
-            const float wcol = cols[n2p];
-            split_stage0_load<C, ZF>(t, g, slot.data(), &wcol, rows, &carry, v);
-            stage0_compute<C, false, true, ZF>(t, v, &twp[size_t(t) * (C::R0 - 1)], &tw0[size_t(t) * 2]);
-            split_stage0_write<C>(t, g, slot.data(), v);
-        }
-    // __syncthreads; stage 1
-    for (int g = 0; g < 2; ++g)
-        for (int t = 0; t < C::T; ++t) {
-            float2* v = &regs[(size_t(g) * C::T + t) * C::E];
-            split_stage1_load<C>(t, g, slot.data(), v);
-            stage1_store<C, false>(t, B.data() + size_t(g) * C::SIZE_B, v, &tw1[size_t(t) * C::C1 * 2]);
-        }
-    // __syncthreads; stage 2, combine twiddle, exchange
-    for (int g = 0; g < 2; ++g)
-        for (int t = 0; t < C::T; ++t) {
-            float2* x = &regs[(size_t(g) * C::T + t) * C::E];
-            stage2<C, false>(t, B.data() + size_t(g) * C::SIZE_B, x);
-            if (g == 1) {
-                const float2 wq = twN[t];
-                split_twiddle_odd<C>(x, &wq);
-            }
-            for (int d = 0; d < C::R2; ++d) XB[size_t(g) * NH + t + C::R0 * C::R1 * d] = x[d];
-        }
-    // __syncthreads; butterfly and fftshift store
-    for (int g = 0; g < 2; ++g)
-        for (int t = 0; t < C::T; ++t) {
-            const float2* x = &regs[(size_t(g) * C::T + t) * C::E];
-            for (int d = 0; d < C::R2; ++d) {
-                const int k = t + C::R0 * C::R1 * d;
-                if (g == 0) out[k + NH] = cadd(x[d], XB[size_t(NH) + k]);          // X[k] stored at (k + N/2) mod N
-                else out[k] = csub(XB[k], x[d]);                                   // X[k + NH] stored at k
-            }
-        }
-}
-
-extern "C" int xmr_emul_fft_split_c64(const float* in, float* out, long long batch, int n_out, int zf, const float* cols,
-                                      const float* rows, const float* twNH, const float* twN) {
-    if (n_out != 8192) return 2;
-    const float2* fin = reinterpret_cast<const float2*>(in);
-    float2* fout = reinterpret_cast<float2*>(out);
-    for (long long b = 0; b < batch; ++b) {
-        const float2* src = fin + b * (n_out / zf);
-        float2* dst = fout + b * n_out;
-        if (zf == 1) emul_split<4096, 1>(src, dst, cols, rows, reinterpret_cast<const float2*>(twNH), reinterpret_cast<const float2*>(twN));
-        else if (zf == 2) emul_split<4096, 2>(src, dst, cols, rows, reinterpret_cast<const float2*>(twNH), reinterpret_cast<const float2*>(twN));
-        else if (zf == 4) emul_split<4096, 4>(src, dst, cols, rows, reinterpret_cast<const float2*>(twNH), reinterpret_cast<const float2*>(twN));
-        else return 2;
     }
     return 0;
 }

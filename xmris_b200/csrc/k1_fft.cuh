@@ -36,7 +36,6 @@ struct K1Params {
     int out_shift;
     float scale;
     const float2* twN;     // exp(-2 pi i k / N), k < N
-    const float2* twH;     // N = 8192 split kernel: the table of the N/2-point transforms
     const float* win;      // table [N] (WIN==1) or column factors [min(N,256)] (WIN==2)
     float win_rows[32];    // row factors (WIN==2)
     float* absmax;

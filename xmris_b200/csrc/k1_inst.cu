@@ -1,9 +1,7 @@
 // One instantiation set of K1 per transform length: compile with -DXMR_N=<N>.
 #include "k1_launch.cuh"
 #include "k1_max.cuh"
-#if XMR_N == 8192
-#include "k1_split.cuh"
-#endif
+
 
 #ifndef XMR_N
 #error "compile with -DXMR_N=<transform length>"
@@ -84,35 +82,6 @@ static cudaError_t launch_max(const K1Params& p, cudaStream_t st) {
 }
 #endif
 
-#if XMR_N == 8192
-template <int ZF, bool PHASE, bool PHDEV>
-static cudaError_t launch_split(const K1Params& p, cudaStream_t st) {
-    auto kern = k1_split_kernel<XMR_N / 2, ZF, PHASE, PHDEV>;
-    constexpr size_t smem = K1SplitSmem<XMR_N / 2>::TOTAL;
-    static thread_local int cached_dev = -1;
-    static thread_local int sms = 0;
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (dev != cached_dev) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-        if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-        cached_dev = dev;
-    }
-    const long long grid = p.batch < sms ? p.batch : sms;      // one persistent CTA (512 threads, ~199 KB) per SM
-    if (grid < 1) return cudaSuccess;
-    kern<<<dim3((unsigned)grid), dim3(2 * FftCfg<XMR_N / 2>::T), smem, st>>>(p);
-    return cudaGetLastError();
-}
-template <int ZF>
-static cudaError_t launch_split_zf(const K1Params& p, cudaStream_t st) {
-    if (p.phase_on != 0 && p.ph_dev != nullptr) return launch_split<ZF, true, true>(p, st);
-    if (p.phase_on != 0) return launch_split<ZF, true, false>(p, st);
-    return launch_split<ZF, false, false>(p, st);
-}
-#endif
 
 #define XMR_CAT2(a, b) a##b
 #define XMR_CAT(a, b) XMR_CAT2(a, b)
@@ -123,16 +92,6 @@ cudaError_t XMR_CAT(k1_launch_, XMR_N)(const K1Params& p, bool inverse, int win,
         // to_fid: no window (scale only -> separable mode with unit rows)
         return tma ? launch_one<XMR_N, true, 2, true>(p, max_ctas, st) : launch_one<XMR_N, true, 2, false>(p, max_ctas, st);
     }
-#if XMR_N == 8192
-    // N = 8192, store variants of the default geometry (input at the start of the row, full / half / quarter length): the
-    // even/odd split kernel -- two interleaved 4096-point transforms, 16 points per thread (k1_split.cuh)
-    if (p.row_slot == nullptr && tma && win == 2 && p.pad_left == 0 && p.in_shift == 0 && p.out_shift == XMR_N / 2 &&
-        p.out != nullptr && p.absmax == nullptr && p.twH != nullptr) {
-        if (p.n_in == XMR_N) return launch_split_zf<1>(p, st);
-        if (2 * p.n_in == XMR_N) return launch_split_zf<2>(p, st);
-        if (4 * p.n_in == XMR_N) return launch_split_zf<4>(p, st);
-    }
-#endif
     // hot path: full-length input, separable window, TMA, fftshift store -> compile-time epilogue variants
     const bool fast_geom = p.row_slot == nullptr && tma && win == 2 && p.n_in == XMR_N && p.pad_left == 0 && p.in_shift == 0 &&
                            p.out_shift == XMR_N / 2 && XMR_N >= 512;

@@ -256,10 +256,6 @@ int k1_dispatch(const void* fid_dev, void* spec_dev, int64_t batch, int n_in, in
     std::memset(&p, 0, sizeof(p));
     int rc = get_twiddles(n_out, &p.twN);
     if (rc != XMR_OK) return rc;
-    if (n_out == 8192) {
-        rc = get_twiddles(4096, &p.twH);
-        if (rc != XMR_OK) return rc;
-    }
     p.in = static_cast<const float2*>(fid_dev);
     p.out = static_cast<float2*>(spec_dev);
     p.batch = batch;
