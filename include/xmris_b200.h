@@ -122,10 +122,11 @@ int64_t xmr_autophase_workspace_bytes(void);
  * Defaults: 6, 15, 4, 4, 2, 2, 2.5 (final spacing 0.01 x 0.024 deg). */
 int xmr_autophase_search_tuning(double p0_step_deg, double p1_step_deg, int starts, int levels, int f32_levels,
                                 int late_starts, double first_ratio);
-/* ACME only: how many mutually distinct basins of the last float32 zoom level are finished by the float64 Newton polish on the
- * analytic gradient of the objective (default 3; 0 = the float64 zoom levels of `levels` instead).  The polish converges
- * to the local minimum to ~1e-4 deg -- where the reference's own optimiser lands when run to convergence. */
-int xmr_autophase_search_polish(int starts);
+/* ACME only: how many mutually distinct basins are finished by the bounded Newton polish on the analytic gradient of the
+ * objective (default 3; 0 = the float64 zoom levels of `levels` instead), how many float32 zoom levels localise them first
+ * (default 1) and whether the finest direct-search level runs for wall-type optima (default 1).  The polish converges to
+ * the local minimum to ~1e-4 deg -- where the reference's own optimiser lands when run to convergence. */
+int xmr_autophase_search_polish(int starts, int f32_levels, int fine_b);
 int xmr_autophase_search_c64(const void* spec_dev, int n, double u0, double du, int method, int target_idx,
                              int index_width, int p0_only, double* result_dev, void* workspace_dev, void* stream);
 

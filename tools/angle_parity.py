@@ -125,6 +125,10 @@ def cmd_gpu(n):
 
     ref = np.load(os.path.join(GOLD, "angle_parity_ref.npz"))
     out = {}
+    if os.environ.get("XMR_POLISH"):           # experiment knob: "starts,f32_levels,fine_b"
+        from xmris_b200 import _lib
+
+        _lib.check(_lib.load().xmr_autophase_search_polish(*[int(v) for v in os.environ["XMR_POLISH"].split(",")]))
     for shape in SHAPES:
         name, fam, n_in, zf, lb, seed = shape
         m = min(n, len(ref[name]))

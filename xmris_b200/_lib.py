@@ -54,7 +54,7 @@ SIGNATURES = {
     "xmr_baseline_als": (_i, [_vp, _i, _vp, _i64, _i, _d, _d, _i, _vp, _i64, _vp]),
     "xmr_autophase_workspace_bytes": (_i64, []),
     "xmr_autophase_search_tuning": (_i, [_d, _d, _i, _i, _i, _i, _d]),
-    "xmr_autophase_search_polish": (_i, [_i]),
+    "xmr_autophase_search_polish": (_i, [_i, _i, _i]),
     "xmr_autophase_search_c64": (_i, [_vp, _i, _d, _d, _i, _i, _i, _i, _vp, _vp, _vp]),
     "xmr_autophase_score_c64": (_i, [_vp, _i, _d, _d, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "xmr_chain_each_c64": (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp, _f, _i, _d, _i, _d, _i, _i, _i,

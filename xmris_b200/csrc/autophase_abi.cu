@@ -334,9 +334,13 @@ int xmr_autophase_search_tuning(double p0_step_deg, double p1_step_deg, int star
     return XMR_OK;
 }
 
-int xmr_autophase_search_polish(int starts) {
-    if (starts < 0 || starts * POLISH_ROLES > ZOOM_MAX_STARTS + 1) return xmr_abi::fail(XMR_ERR_BAD_ARG, "polish starts=%d must lie in [0, %d]", starts, (ZOOM_MAX_STARTS + 1) / POLISH_ROLES);
+int xmr_autophase_search_polish(int starts, int f32_levels, int fine_b) {
+    if (starts < 0 || starts * POLISH_ROLES > ZOOM_MAX_STARTS + 1 || f32_levels < 0 || f32_levels > 4)
+        return xmr_abi::fail(XMR_ERR_BAD_ARG, "polish starts=%d must lie in [0, %d], f32_levels=%d in [0, 4]", starts,
+                             (ZOOM_MAX_STARTS + 1) / POLISH_ROLES, f32_levels);
     g_tuning.polish_starts = starts;
+    g_tuning.polish_f32_levels = f32_levels;
+    g_tuning.fine_b = fine_b ? 1 : 0;
     return XMR_OK;
 }
 
