@@ -33,6 +33,7 @@ constexpr int K2A_MAXIT = 16;
 constexpr float K2A_ROWSTEP = 45.f;
 constexpr float K2A_L2_DP1 = 15.f;   // L2 rows: cell.p1 + {-15, 0, 15}
 constexpr float K2A_L2_DP0 = 2.5f;   // L2 p0 candidates: cell.p0 + (k - 3.5) * 2.5
+constexpr float K2A_SIBLING = 20.f;  // sibling starts: result.p1 -+ 20 deg
 
 template <int N>
 struct K2aSmem {
@@ -41,9 +42,9 @@ struct K2aSmem {
     static constexpr size_t SLOT = size_t(C::N) * sizeof(float2);
     static constexpr size_t SPN = (size_t(C::N) + (size_t(C::N) >> PADSHIFT) + 2);
     static constexpr size_t B = (C::SIZE_B > SPN ? size_t(C::SIZE_B) : SPN) * sizeof(float2);
-    static constexpr size_t DEC = size_t(K2A_NDEC) * (sizeof(float2) + sizeof(float));
+    static constexpr size_t DEC = size_t(K2A_NDEC + K2A_NDEC / 8) * (sizeof(float2) + sizeof(float));
     static constexpr size_t ROWS = size_t(192) * 2 * sizeof(float);
-    static constexpr size_t MISC = 8192;
+    static constexpr size_t MISC = 12288;
     static constexpr size_t TOTAL = SLOT + B + DEC + ROWS + MISC;
 };
 
@@ -53,7 +54,7 @@ struct K2aShared {      // lives in the MISC area
     int redi[32];
     float cell_p0[K2A_T], cell_p1[K2A_T];
     float l2f[K2A_T * 3], l2p0[K2A_T * 3], l2p1[K2A_T * 3];
-    float part[K2A_NS][8][3][GRAD_NSUMS];     // [start][segment][evaluation point][sum] (per-warp float32 partial sums)
+    double part[K2A_NS][8][3][GRAD_NSUMS];    // [start][segment][evaluation point][sum] (per-warp partial sums)
     int gs;                                   // segments (warps) per active start in this iteration
     double y0[K2A_NS], y1[K2A_NS];            // trial point per start
     int np[K2A_NS];                           // evaluation points wanted at the trial point: 1 (gradient) or 3 (+ secant Hessian)
@@ -66,7 +67,7 @@ struct K2aShared {      // lives in the MISC area
     float zc0, zc1, zcf;
     int wall;
 };
-static_assert(sizeof(K2aShared) <= 8192, "K2aShared must fit the MISC area");
+static_assert(sizeof(K2aShared) <= 12288, "K2aShared must fit the MISC area");
 
 template <int N>
 __global__ void __launch_bounds__(FftCfg<N>::T, (N >= 8192 ? 1 : (FftCfg<N>::T >= 256 ? 2 : (FftCfg<N>::T >= 128 ? 4 : 8))))
@@ -86,7 +87,7 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
     float2* Bbuf = reinterpret_cast<float2*>(smem_raw + SM::SLOT);
     float2* sp = Bbuf;                                                     // padded spectrum reuses exchange B
     float2* zdec = reinterpret_cast<float2*>(smem_raw + SM::SLOT + SM::B);
-    float* r2dec = reinterpret_cast<float*>(zdec + K2A_NDEC);
+    float* r2dec = reinterpret_cast<float*>(zdec + K2A_NDEC + K2A_NDEC / 8);
     float* rowf = reinterpret_cast<float*>(smem_raw + SM::SLOT + SM::B + SM::DEC);
     float* rowp0 = rowf + 192;
     K2aShared& sh = *reinterpret_cast<K2aShared*>(smem_raw + SM::SLOT + SM::B + SM::DEC + SM::ROWS);
@@ -226,14 +227,15 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
             const float2 S = sp[m + (m >> PADSHIFT)];
             const float r2 = S.x * S.x + S.y * S.y;
             const float inv = r2 > 0.f ? rsqrtf(r2) : 0.f;
-            zdec[j] = make_float2(S.x * inv, S.y * inv);
-            r2dec[j] = r2;
+            zdec[j + (j >> 3)] = make_float2(S.x * inv, S.y * inv);       // one pad element per lane chunk of 8: conflict-free
+            r2dec[j + (j >> 3)] = r2;
         }
         __syncthreads();
         constexpr int PPL = K2A_NDEC / 32;                     // decimated points per lane (contiguous)
+        static_assert(PPL == 8, "the padding rule j + (j >> 3) assumes 8 decimated points per lane");
         float F0 = 0.f;
 #pragma unroll
-        for (int i = 0; i < PPL; ++i) F0 += r2dec[lane * PPL + i];
+        for (int i = 0; i < PPL; ++i) F0 += r2dec[lane * (PPL + 1) + i];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) F0 += __shfl_xor_sync(0xffffffffu, F0, off);
         const int nrows = p.p0_only ? 1 : K2_NP1;
@@ -252,8 +254,8 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
             float f1x = 0.f, f1y = 0.f, f2x = 0.f, f2y = 0.f, f3x = 0.f, f3y = 0.f, f5x = 0.f, f5y = 0.f;
 #pragma unroll
             for (int i = 0; i < PPL; ++i) {
-                const float2 z = zdec[lane * PPL + i];
-                const float w = r2dec[lane * PPL + i];
+                const float2 z = zdec[lane * (PPL + 1) + i];
+                const float w = r2dec[lane * (PPL + 1) + i];
                 const float ax = z.x * cr - z.y * sr, ay = z.x * sr + z.y * cr;        // unit phasor of the rotated point
                 const float bx = ax * ax - ay * ay, by = 2.f * ax * ay;                // ^2
                 const float cx = bx * ax - by * ay, cy = bx * ay + by * ax;            // ^3
@@ -433,13 +435,73 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
 
         // ---- F: L3, bounded quasi-Newton on the analytic gradient ---------------------------------------------------------
         // Newton state of start s lives in thread s (t < K2A_NS); the walks are spread over (start, segment) slots.
+        // Phase 0 refines the L2 starts.  Phase 1 ("siblings"): a valley often holds a second minimum 10-30 deg of p1 away
+        // (two branches of max(d) meet); two more starts, 20 deg of p1 either side of the phase-0 result with p0 re-scanned
+        // there, either fall back into it (and are merged after an iteration or two) or find the sibling.
+        const double p1_lo = p.p0_only ? 0.0 : -4000.0, p1_hi = p.p0_only ? 0.0 : 4000.0;
+        for (int phase = 0; phase < (p.p0_only ? 1 : 2); ++phase) {
+        if (phase == 1) {
+            if (t == 0) {
+                int bs = 0;
+                for (int s = 1; s < K2A_NS; ++s)
+                    if (sh.res_f[s] < sh.res_f[bs]) bs = s;
+                sh.res_f[0] = sh.res_f[bs]; sh.res_p0[0] = sh.res_p0[bs]; sh.res_p1[0] = sh.res_p1[bs];
+                sh.res_h[0] = sh.res_h[bs]; sh.res_pen[0] = sh.res_pen[bs];
+            }
+            __syncthreads();
+            for (int w = warp; w < 2; w += WPS) {
+                const float c0c = float(sh.res_p0[0]);
+                const float p1 = fminf(fmaxf(float(sh.res_p1[0]) + (w == 0 ? -K2A_SIBLING : K2A_SIBLING), -4000.f), 4000.f);
+                float c0[K2_K], s0[K2_K], p0k[K2_K];
+#pragma unroll
+                for (int k = 0; k < K2_K; ++k) {
+                    float q0 = c0c + (float(k) - 3.5f) * K2A_L2_DP0;
+                    q0 = q0 > 180.f ? q0 - 360.f : (q0 < -180.f ? q0 + 360.f : q0);
+                    p0k[k] = q0;
+                    sincospif(q0 * (1.0f / 180.0f), &s0[k], &c0[k]);
+                }
+                Acc<float, METHOD_ACME, K2_K> acc;
+                acc.init();
+                lane_accumulate_rt<float, METHOD_ACME, K2_K>(sp, PADSHIFT, lane * L, (lane + 1) * L, geom, p1 * (1.0f / 360.0f), u0, duf, c0, s0, acc);
+                acc.warp_reduce();
+                float rbf = CUDART_INF_F, rb0 = c0c;
+#pragma unroll
+                for (int k = 0; k < K2_K; ++k) {
+                    const float f = acc.score(k, geom);
+                    if (f < rbf) { rbf = f; rb0 = p0k[k]; }
+                }
+                if (lane == 0) { sh.zf[w] = rbf; sh.zp0[w] = rb0; sh.zp1[w] = p1; }
+            }
+            __syncthreads();
+            if (t == 0) {
+                int any = 0;
+                sh.active[0] = 0;
+                for (int s = 1; s < K2A_NS; ++s) {
+                    const int w = s - 1;
+                    const bool ok = w < 2 && sh.res_f[0] < CUDART_INF && sh.zf[w] < CUDART_INF_F &&
+                                    fabs(double(sh.zp1[w]) - sh.res_p1[0]) > 5.0;      // (clamped at the box edge: no sibling there)
+                    sh.y0[s] = double(sh.zp0[w]);
+                    sh.y1[s] = double(sh.zp1[w]);
+                    sh.np[s] = 3;
+                    sh.active[s] = ok ? 1 : 0;
+                    sh.res_f[s] = ok ? double(sh.zf[w]) : CUDART_INF;
+                    sh.res_p0[s] = sh.y0[s];
+                    sh.res_p1[s] = sh.y1[s];
+                    any |= sh.active[s];
+                }
+                sh.any_active = any;
+                int nact = 0;
+                for (int s = 0; s < K2A_NS; ++s) nact += sh.active[s];
+                sh.gs = nact <= 1 ? GSMAX : (nact == 2 ? (GSMAX >= 2 ? GSMAX / 2 : 1) : (GSMAX >= 4 ? GSMAX / 4 : 1));
+            }
+            __syncthreads();
+        }
         NewtonState st;
         st.x0 = st.x1 = 0.0; st.f = CUDART_INF; st.g0 = st.g1 = 0.0; st.done = 0; st.iters = 0;
         double h00 = 0.0, h01 = 0.0, h11 = 0.0;         // current Hessian model (per degree^2)
         double stp0 = 0.0, stp1 = 0.0;                  // last proposed step
         int rejects = 0, refreshed = 0;
         double res_h = 1.0, res_pen = 0.0;
-        const double p1_lo = p.p0_only ? 0.0 : -4000.0, p1_hi = p.p0_only ? 0.0 : 4000.0;
         for (int nit = 0; nit < K2A_MAXIT && sh.any_active; ++nit) {
             // the warps are shared out among the ACTIVE starts: 8 warps -> 2 per start while three run, 4 while two, all 8 for
             // the last one (most voxels: the starts merge after two or three iterations)
@@ -467,16 +529,17 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
                     double ta = q0 / 360.0 + (q1 / 360.0) * um0;
                     ta -= floor(ta);
                     lane_grad<float, 16>(sp, PADSHIFT, m0, m1, N, float(ta), float(q1 / 360.0), float(-p.du * double(m0)), duf, -1, a);
-                    a.gP1 += float(um0) * a.gP0;        // u restarts at 0 inside the chunk: shift the u-weighted sums back
-                    a.As1 += float(um0) * a.As0;
-                    a.Al1 += float(um0) * a.Al0;
-                    a.umax += float(um0);
-                    a.warp_reduce();
-                    if (lane == 0) {
-                        float* o = sh.part[s][g][k];
-                        o[0] = a.P; o[1] = a.gP0; o[2] = a.gP1; o[3] = a.G2; o[4] = a.T2; o[5] = a.As0; o[6] = a.As1; o[7] = a.Al0;
-                        o[8] = a.Al1; o[9] = a.dmax; o[10] = a.qmax; o[11] = a.umax;
-                    }
+                    // float32 only WITHIN the lane's short chunk: the chunk sums go to float64 before they are combined (where
+                    // the penalty is large the gradient is a small difference of large sums; float32 lane-to-lane adds left the
+                    // minimum 0.1-0.2 deg short along the flat valley)
+                    GradSums<double> ad;
+                    ad.P = a.P; ad.gP0 = a.gP0; ad.G2 = a.G2; ad.T2 = a.T2; ad.As0 = a.As0; ad.Al0 = a.Al0;
+                    ad.gP1 = double(a.gP1) + um0 * double(a.gP0);      // u restarts at 0 inside the chunk: shift the u-weighted sums back
+                    ad.As1 = double(a.As1) + um0 * double(a.As0);
+                    ad.Al1 = double(a.Al1) + um0 * double(a.Al0);
+                    ad.dmax = a.dmax; ad.qmax = a.qmax; ad.umax = double(a.umax) + um0;
+                    ad.warp_reduce();
+                    if (lane == 0) grad_store(ad, sh.part[s][g][k]);
                 }
             }
             __syncthreads();
@@ -487,13 +550,7 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
                 for (int k = 0; k < np; ++k) {
                     GradSums<double> tot;
                     tot.init();
-                    for (int g = 0; g < sh.gs; ++g) {
-                        const float* o = sh.part[s][g][k];
-                        GradSums<double> pg;
-                        pg.P = o[0]; pg.gP0 = o[1]; pg.gP1 = o[2]; pg.G2 = o[3]; pg.T2 = o[4]; pg.As0 = o[5]; pg.As1 = o[6];
-                        pg.Al0 = o[7]; pg.Al1 = o[8]; pg.dmax = o[9]; pg.qmax = o[10]; pg.umax = o[11];
-                        tot.merge(pg);
-                    }
+                    for (int g = 0; g < sh.gs; ++g) tot.merge(grad_load(sh.part[s][g][k]));
                     r[k] = acme_finish(tot, N);
                 }
                 const double y0 = sh.y0[s], y1 = sh.y1[s];
@@ -561,7 +618,6 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
                     if (last) {
                         st.x0 += stp0;
                         st.x1 = t1;
-                        st.f *= (1.0 - 1e-12);          // (recorded below as the start's result; the value moves by < 1e-7)
                         sh.active[s] = 0;
                     } else if (!(st.f < CUDART_INF) || conv) {
                         sh.active[s] = 0;
@@ -587,7 +643,9 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
                         sh.active[s] = 0;
                     }
                 }
-                if (st.f < sh.res_f[s] || st.iters == 1) {
+                // the start's result is its ACCEPTED iterate: near convergence the objective changes by less than its float32
+                // noise, so "record only if f decreased" would freeze the answer one or two (0.1 deg) steps early
+                if (st.iters >= 1) {
                     sh.res_f[s] = st.f; sh.res_p0[s] = st.x0; sh.res_p1[s] = st.x1;
                     sh.res_h[s] = res_h; sh.res_pen[s] = res_pen;
                 }
@@ -615,6 +673,7 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
             }
             __syncthreads();
         }
+        }   // phase
         double fin_f = CUDART_INF, fin_p0 = 0.0, fin_p1 = 0.0;
         {
             int bs = 0;
