@@ -129,6 +129,11 @@ def cmd_gpu(n):
         from xmris_b200 import _lib
 
         _lib.check(_lib.load().xmr_autophase_search_polish(*[int(v) for v in os.environ["XMR_POLISH"].split(",")]))
+    if os.environ.get("XMR_TUNING"):           # experiment knob: "p0_step,p1_step,starts,levels,f32_levels,late_starts,first_ratio"
+        from xmris_b200 import _lib
+
+        v = os.environ["XMR_TUNING"].split(",")
+        _lib.check(_lib.load().xmr_autophase_search_tuning(float(v[0]), float(v[1]), int(v[2]), int(v[3]), int(v[4]), int(v[5]), float(v[6])))
     for shape in SHAPES:
         name, fam, n_in, zf, lb, seed = shape
         m = min(n, len(ref[name]))
