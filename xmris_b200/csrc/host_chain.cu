@@ -187,6 +187,17 @@ int xmr_chain_host_c64(const xmr_host_chain_desc* d, const void* fid_host, void*
     const size_t o_sws = align_up(o_row + row_out + 64, 256);
     const size_t small = o_sws + size_t(xmr_autophase_workspace_bytes());
     const bool keep_all_in = (d->autophase_mode == 1);                     // the FIDs are read twice
+    if (keep_all_in) {
+        // mode="single" keeps the whole FID batch on the device between its two passes: say so instead of failing inside
+        // cudaMalloc when it cannot fit (the workspace is cached per thread; xmr_host_workspace_release() returns it)
+        size_t free_b = 0, total_b = 0;
+        XMR_CU(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = size_t(batch) * row_in + 2 * size_t(chunk) * row_out + small;
+        if (need > free_b + g_ws.d_in_bytes + 2 * g_ws.d_out_bytes + g_ws.d_small_bytes)
+            return xmr_abi::fail(XMR_ERR_BAD_ARG, "host chain (mode=single) needs %.1f GB of device memory for %lld FIDs, %.1f GB are free: "
+                                 "split the batch (the global |S| maximum then has to be taken over the parts by the caller) or use the "
+                                 "device-resident entry points", need / 1e9, (long long)batch, free_b / 1e9);
+    }
     int rc = ensure_workspace(keep_all_in ? size_t(batch) * row_in : 2 * size_t(chunk) * row_in, size_t(chunk) * row_out, small);
     if (rc != XMR_OK) return rc;
     Workspace& w = g_ws;
@@ -216,18 +227,31 @@ int xmr_chain_host_c64(const xmr_host_chain_desc* d, const void* fid_host, void*
     }
     const float scale = d->scale != 0.f ? d->scale : 1.0f / std::sqrt(float(n_out));
     const int64_t nchunks = (batch + chunk - 1) / chunk;
-    std::vector<cudaEvent_t> in_done(nchunks);
-    for (auto& e : in_done) XMR_CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    std::vector<cudaEvent_t> in_done(nchunks, nullptr);
     cudaEvent_t out_free[2] = {nullptr, nullptr}, cmp_done[2] = {nullptr, nullptr}, in_free[2] = {nullptr, nullptr};
-    for (int i = 0; i < 2; ++i) {
-        XMR_CU(cudaEventCreateWithFlags(&out_free[i], cudaEventDisableTiming));
-        XMR_CU(cudaEventCreateWithFlags(&cmp_done[i], cudaEventDisableTiming));
-        XMR_CU(cudaEventCreateWithFlags(&in_free[i], cudaEventDisableTiming));
-    }
-    auto cleanup = [&]() {
-        for (auto& e : in_done) cudaEventDestroy(e);
-        for (int i = 0; i < 2; ++i) { cudaEventDestroy(out_free[i]); cudaEventDestroy(cmp_done[i]); cudaEventDestroy(in_free[i]); }
+    auto cleanup = [&]() {          // (also reached when an event creation below fails: destroys what exists)
+        for (auto& e : in_done)
+            if (e) cudaEventDestroy(e);
+        for (int i = 0; i < 2; ++i) {
+            if (out_free[i]) cudaEventDestroy(out_free[i]);
+            if (cmp_done[i]) cudaEventDestroy(cmp_done[i]);
+            if (in_free[i]) cudaEventDestroy(in_free[i]);
+        }
     };
+    {
+        cudaError_t ee = cudaSuccess;
+        for (auto& e : in_done)
+            if (ee == cudaSuccess) ee = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        for (int i = 0; i < 2 && ee == cudaSuccess; ++i) {
+            ee = cudaEventCreateWithFlags(&out_free[i], cudaEventDisableTiming);
+            if (ee == cudaSuccess) ee = cudaEventCreateWithFlags(&cmp_done[i], cudaEventDisableTiming);
+            if (ee == cudaSuccess) ee = cudaEventCreateWithFlags(&in_free[i], cudaEventDisableTiming);
+        }
+        if (ee != cudaSuccess) {
+            cleanup();
+            return xmr_abi::cuda_fail(ee, "cudaEventCreateWithFlags");
+        }
+    }
     const unsigned char* h_in = static_cast<const unsigned char*>(fid_host);
     unsigned char* h_out = static_cast<unsigned char*>(out_host);
     unsigned char* d_in = static_cast<unsigned char*>(w.d_in);
