@@ -116,3 +116,38 @@ def test_autophase_mode_all_accessor():
         s = sp.values[r, 0].astype(np.complex128)
         _, i = orc.autophase(s, 0, freqs, method="positivity", peak_width=100, p0_only=True)
         assert abs(o2.coords["phase_p0"].values[r, 0] - i["p0"]) < ANG
+
+
+@pytest.mark.parametrize("variant", ["p0_only", "target_coord"])
+def test_mode_all_acme_variants_against_per_spectrum_reference(variant):
+    """K2-ACME with ``p0_only=True`` (one-parameter search, p1 = 0) and with ``target_coord`` (fixed, off-grid pivot for every
+    voxel: phasing.py:233-235): each voxel against the reference's autophase on that 1-D spectrum -- angles within 0.1 deg or an
+    objective not worse; spectra equal to the reference's phase() at the GPU's angles."""
+    import xmris_b200
+    from xmris_b200.synth import make_fids_numpy
+
+    nvox = 20
+    fid, t, _ = make_fids_numpy("13C", nvox, 1024, seed=77)
+    da = xmris_b200.xr.DataArray(fid.astype(np.complex64), dims=["vox", "time"], coords={"time": t})
+    sp = da.xmr.apodize_exp(lb=10.0).xmr.to_spectrum()
+    freqs = sp.coords["frequency"].values
+    kw = dict(p0_only=True) if variant == "p0_only" else dict(target_coord=-120.3)
+    out = sp.xmr.autophase(mode="all", **kw)
+    p0, p1, piv = (out.coords[k].values for k in ("phase_p0", "phase_p1", "phase_pivot"))
+    ref_spec = np.asarray(sp.values, dtype=np.complex128)
+    ref = _reference(ref_spec, freqs, dict(peak_width=100, **kw))
+    worse = 0
+    for i in range(nvox):
+        assert piv[i] == ref[i, 2], (i, piv[i], ref[i, 2])
+        if variant == "p0_only":
+            assert p1[i] == 0.0
+        same, _ = orc.phase(ref_spec[i], 0, freqs, p0[i], p1[i], piv[i])
+        assert rel_l2(out.values[i], same) < 2e-5
+        ph = [p0[i]] if variant == "p0_only" else [p0[i], p1[i]]
+        f_gpu = orc.acme_score(ph, ref_spec[i], freqs, piv[i])
+        d0 = abs(((p0[i] - ref[i, 0] + 180.0) % 360.0) - 180.0)
+        close = d0 <= ANG and abs(p1[i] - ref[i, 1]) <= ANG
+        if not (close or f_gpu <= ref[i, 3] * (1 + 1e-5)):
+            worse += 1
+            print(f"{variant} voxel {i}: gpu ({p0[i]:.3f}, {p1[i]:.3f}) f={f_gpu:.6g}  ref ({ref[i,0]:.3f}, {ref[i,1]:.3f}) f={ref[i,3]:.6g}")
+    assert worse <= 1, worse
