@@ -3,6 +3,7 @@
 #include "k1_max.cuh"
 
 
+
 #ifndef XMR_N
 #error "compile with -DXMR_N=<transform length>"
 #endif
@@ -81,6 +82,7 @@ static cudaError_t launch_max(const K1Params& p, cudaStream_t st) {
     return cudaGetLastError();
 }
 #endif
+
 
 
 #define XMR_CAT2(a, b) a##b
