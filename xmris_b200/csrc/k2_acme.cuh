@@ -25,7 +25,8 @@
 
 namespace xmr {
 
-constexpr int K2A_NDEC = 256;      // decimated points of the L1 stage
+constexpr int K2A_NDEC = 256;      // blocks of the L1 stage (block moments of N / 256 points each)
+constexpr int K2A_GSTRIDE = K2A_NDEC + K2A_NDEC / 8 + 8;   // padded length of one moment array
 constexpr int K2A_NP0 = 64;        // L1 p0 grid: -180 + 5.625 k
 constexpr int K2A_T = 6;           // L1 cells handed to L2
 constexpr int K2A_NS = 3;          // L2 cells handed to the Newton refinement
@@ -42,7 +43,7 @@ struct K2aSmem {
     static constexpr size_t SLOT = size_t(C::N) * sizeof(float2);
     static constexpr size_t SPN = (size_t(C::N) + (size_t(C::N) >> PADSHIFT) + 2);
     static constexpr size_t B = (C::SIZE_B > SPN ? size_t(C::SIZE_B) : SPN) * sizeof(float2);
-    static constexpr size_t DEC = size_t(K2A_NDEC + K2A_NDEC / 8) * (sizeof(float2) + sizeof(float));
+    static constexpr size_t DEC = size_t(4) * K2A_GSTRIDE * sizeof(float2);     // block moments G_1, G_2, G_3, G_5
     static constexpr size_t ROWS = size_t(192) * 2 * sizeof(float);
     static constexpr size_t MISC = 12288;
     static constexpr size_t TOTAL = SLOT + B + DEC + ROWS + MISC;
@@ -86,8 +87,7 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
     float2* slot = reinterpret_cast<float2*>(smem_raw);
     float2* Bbuf = reinterpret_cast<float2*>(smem_raw + SM::SLOT);
     float2* sp = Bbuf;                                                     // padded spectrum reuses exchange B
-    float2* zdec = reinterpret_cast<float2*>(smem_raw + SM::SLOT + SM::B);
-    float* r2dec = reinterpret_cast<float*>(zdec + K2A_NDEC + K2A_NDEC / 8);
+    float2* gdec = reinterpret_cast<float2*>(smem_raw + SM::SLOT + SM::B);
     float* rowf = reinterpret_cast<float*>(smem_raw + SM::SLOT + SM::B + SM::DEC);
     float* rowp0 = rowf + 192;
     K2aShared& sh = *reinterpret_cast<K2aShared*>(smem_raw + SM::SLOT + SM::B + SM::DEC + SM::ROWS);
@@ -221,30 +221,64 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
         const float upiv = u0 + duf * float(mstar);
         const float apiv = sqrtf(Spiv.x * Spiv.x + Spiv.y * Spiv.y);
 
-        // ---- D: L1, series surrogate of the penalty term on the decimated spectrum --------------------------------------
-        for (int j = t; j < K2A_NDEC; j += C::T) {
-            const int m = DEC * j;
-            const float2 S = sp[m + (m >> PADSHIFT)];
-            const float r2 = S.x * S.x + S.y * S.y;
-            const float inv = r2 > 0.f ? rsqrtf(r2) : 0.f;
-            zdec[j + (j >> 3)] = make_float2(S.x * inv, S.y * inv);       // one pad element per lane chunk of 8: conflict-free
-            r2dec[j + (j >> 3)] = r2;
+        // ---- D: L1, series surrogate of the penalty term from BLOCK MOMENTS of the whole spectrum ------------------------------
+        // G_k[b] = sum over the DEC points m of block b of r_m^2 e^{i k theta_m}, k = 1, 2, 3, 5 (every point contributes: narrow
+        // peaks are not stepped over), F_0 = sum r^2.  Per row, F_k(p1) = sum_b G_k[b] e^{i k p1 u_b} with u at the block centre
+        // (the first-order phase varies by < p1*du*DEC/2 <= 8 deg inside a block).
+        {
+            constexpr int LG = ilog2(DEC);
+            float f0acc = 0.f;
+            for (int base = warp * 32; base < N; base += C::T) {           // 32 consecutive points per warp step: conflict-free
+                const int m = base + lane;
+                const float2 S = sp[m + (m >> PADSHIFT)];
+                const float r2 = S.x * S.x + S.y * S.y;
+                const float inv = r2 > 0.f ? rsqrtf(r2) : 0.f;
+                const float zx = S.x * inv, zy = S.y * inv;                    // e^{i theta}
+                const float bx = zx * zx - zy * zy, by = 2.f * zx * zy;        // ^2
+                const float cx = bx * zx - by * zy, cy = bx * zy + by * zx;    // ^3
+                const float ex = bx * cx - by * cy, ey = bx * cy + by * cx;    // ^5
+                float g[8] = {r2 * zx, r2 * zy, r2 * bx, r2 * by, r2 * cx, r2 * cy, r2 * ex, r2 * ey};
+                f0acc += r2;
+#pragma unroll
+                for (int s = 0; s < (LG < 5 ? LG : 5); ++s)                     // segmented sum over the DEC lanes of a block
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) g[q] += __shfl_xor_sync(0xffffffffu, g[q], 1 << s);
+                if (DEC >= 32) {
+                    // a block spans DEC/32 warp steps: accumulate in shared memory (one warp owns a block at a time)
+                    const int b = m / DEC;
+                    if (lane == 0) {
+                        const bool first = (m % DEC) == 0;
+                        float2* gp = gdec + (b + (b >> 3));
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float2 cur = first ? make_float2(0.f, 0.f) : gp[q * K2A_GSTRIDE];
+                            gp[q * K2A_GSTRIDE] = make_float2(cur.x + g[2 * q], cur.y + g[2 * q + 1]);
+                        }
+                    }
+                } else if ((lane & (DEC - 1)) == 0) {
+                    const int b = m / DEC;
+                    float2* gp = gdec + (b + (b >> 3));
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) gp[q * K2A_GSTRIDE] = make_float2(g[2 * q], g[2 * q + 1]);
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) f0acc += __shfl_xor_sync(0xffffffffu, f0acc, off);
+            if (lane == 0) sh.redv[warp] = f0acc;
         }
         __syncthreads();
-        constexpr int PPL = K2A_NDEC / 32;                     // decimated points per lane (contiguous)
-        static_assert(PPL == 8, "the padding rule j + (j >> 3) assumes 8 decimated points per lane");
+        constexpr int PPL = K2A_NDEC / 32;                     // blocks per lane (contiguous)
+        static_assert(PPL == 8, "the padding rule b + (b >> 3) assumes 8 blocks per lane");
         float F0 = 0.f;
 #pragma unroll
-        for (int i = 0; i < PPL; ++i) F0 += r2dec[lane * (PPL + 1) + i];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) F0 += __shfl_xor_sync(0xffffffffu, F0, off);
+        for (int w = 0; w < WPS; ++w) F0 += sh.redv[w];
         const int nrows = p.p0_only ? 1 : K2_NP1;
         for (int r = warp; r < nrows; r += WPS) {
             const float p1 = p.p0_only ? 0.f : fminf(-4000.f + K2A_ROWSTEP * float(r), 4000.f);
             const float tpu = p1 * (1.0f / 360.0f);
             float sr, cr, ss, cs;
             {
-                float ta = tpu * (u0 + duf * float(DEC * lane * PPL));
+                float ta = tpu * (u0 + duf * (float(DEC * lane * PPL) + 0.5f * float(DEC - 1)));      // centre of the lane's first block
                 ta -= floorf(ta);
                 sincospif(2.0f * ta, &sr, &cr);
                 float ts = tpu * duf * float(DEC);
@@ -254,16 +288,15 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
             float f1x = 0.f, f1y = 0.f, f2x = 0.f, f2y = 0.f, f3x = 0.f, f3y = 0.f, f5x = 0.f, f5y = 0.f;
 #pragma unroll
             for (int i = 0; i < PPL; ++i) {
-                const float2 z = zdec[lane * (PPL + 1) + i];
-                const float w = r2dec[lane * (PPL + 1) + i];
-                const float ax = z.x * cr - z.y * sr, ay = z.x * sr + z.y * cr;        // unit phasor of the rotated point
-                const float bx = ax * ax - ay * ay, by = 2.f * ax * ay;                // ^2
-                const float cx = bx * ax - by * ay, cy = bx * ay + by * ax;            // ^3
+                const float2* gp = gdec + lane * (PPL + 1) + i;
+                const float2 g1 = gp[0], g2 = gp[K2A_GSTRIDE], g3 = gp[2 * K2A_GSTRIDE], g5 = gp[3 * K2A_GSTRIDE];
+                const float bx = cr * cr - sr * sr, by = 2.f * cr * sr;                // e^{2 i p1 u_b}
+                const float cx = bx * cr - by * sr, cy = bx * sr + by * cr;            // ^3
                 const float ex = bx * cx - by * cy, ey = bx * cy + by * cx;            // ^5
-                f1x = fmaf(w, ax, f1x); f1y = fmaf(w, ay, f1y);
-                f2x = fmaf(w, bx, f2x); f2y = fmaf(w, by, f2y);
-                f3x = fmaf(w, cx, f3x); f3y = fmaf(w, cy, f3y);
-                f5x = fmaf(w, ex, f5x); f5y = fmaf(w, ey, f5y);
+                f1x = fmaf(g1.x, cr, fmaf(-g1.y, sr, f1x)); f1y = fmaf(g1.x, sr, fmaf(g1.y, cr, f1y));
+                f2x = fmaf(g2.x, bx, fmaf(-g2.y, by, f2x)); f2y = fmaf(g2.x, by, fmaf(g2.y, bx, f2y));
+                f3x = fmaf(g3.x, cx, fmaf(-g3.y, cy, f3x)); f3y = fmaf(g3.x, cy, fmaf(g3.y, cx, f3y));
+                f5x = fmaf(g5.x, ex, fmaf(-g5.y, ey, f5x)); f5y = fmaf(g5.x, ey, fmaf(g5.y, ex, f5y));
                 const float ncr = cr * cs - sr * ss;
                 sr = cr * ss + sr * cs;
                 cr = ncr;
