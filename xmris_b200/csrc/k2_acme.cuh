@@ -28,7 +28,10 @@ namespace xmr {
 constexpr int K2A_NDEC = 256;      // blocks of the L1 stage (block moments of N / 256 points each)
 constexpr int K2A_GSTRIDE = K2A_NDEC + K2A_NDEC / 8 + 8;   // padded length of one moment array
 constexpr int K2A_NP0 = 64;        // L1 p0 grid: -180 + 5.625 k
-constexpr int K2A_T = 6;           // L1 cells handed to L2
+#ifndef XMR_K2A_T
+#define XMR_K2A_T 6
+#endif
+constexpr int K2A_T = XMR_K2A_T;   // L1 cells handed to L2 (6: 3 rows for the best four + 2 rows for the others = 16 walks; 4: 12 walks)
 constexpr int K2A_NS = 3;          // L2 cells handed to the Newton refinement
 constexpr int K2A_MAXIT = 16;
 constexpr float K2A_ROWSTEP = 45.f;
@@ -394,7 +397,7 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
         // ---- E: L2, the true objective around the K2A_T cells (full spectrum, 3 p1 rows x 8 p0 per cell) ----------------
         // 3 rows (cell.p1 - 15, 0, + 15) for the four best cells, 2 rows (-+ 7.5) for the other two: 16 walks = two full rounds
         // of 8 warps
-        const int l2items = p.p0_only ? K2A_T : 16;
+        const int l2items = p.p0_only ? K2A_T : (K2A_T >= 6 ? 16 : 3 * K2A_T);
         for (int item = warp; item < l2items; item += WPS) {
             const int cell = p.p0_only ? item : (item < 12 ? item / 3 : 4 + (item - 12) / 2);
             const int rr = p.p0_only ? 0 : (item < 12 ? item % 3 : (item - 12) % 2);
@@ -472,7 +475,10 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
         // (two branches of max(d) meet); two more starts, 20 deg of p1 either side of the phase-0 result with p0 re-scanned
         // there, either fall back into it (and are merged after an iteration or two) or find the sibling.
         const double p1_lo = p.p0_only ? 0.0 : -4000.0, p1_hi = p.p0_only ? 0.0 : 4000.0;
-        for (int phase = 0; phase < (p.p0_only ? 1 : 2); ++phase) {
+#ifndef XMR_K2A_PHASES
+#define XMR_K2A_PHASES 2
+#endif
+        for (int phase = 0; phase < (p.p0_only ? 1 : XMR_K2A_PHASES); ++phase) {
         if (phase == 1) {
             if (t == 0) {
                 int bs = 0;
