@@ -25,10 +25,10 @@ pytestmark = pytest.mark.gpu
 
 # shape -> (floor of match % incl. adjudicated [single, all], ceiling of worse % [single, all])
 FLOORS = {
-    "C2_2048": ((98.5, 96.0), (1.5, 4.0)),
-    "C3_4096_zf8192": ((98.5, 97.5), (1.5, 2.5)),
-    "C4_13C_1024": ((99.0, 99.0), (1.0, 1.0)),
-    "C5_4096": ((98.5, 97.5), (1.5, 2.5)),
+    "C2_2048": ((98.5, 98.0), (1.5, 2.0)),
+    "C3_4096_zf8192": ((98.5, 98.5), (1.5, 1.5)),
+    "C4_13C_1024": ((99.0, 99.5), (1.0, 0.5)),
+    "C5_4096": ((98.5, 98.5), (1.5, 1.5)),
 }
 N = 1024
 
