@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_zoom_kernel(const __gri
     const int per_warp = (n + NW - 1) / NW;
     const int L = (per_warp + 31) / 32;
     const int padshift = ilog2_ceil(L);
-    load_padded(sp, p.spec, n, padshift);
+    if (!p.only_flagged) load_padded(sp, p.spec, n, padshift);   // (flagged-only levels decide first: most CTAs only pass their centre on)
     const int per_start = p.rows * (ZOOM_SPAN / K);
     const int start = blockIdx.x / per_start, local = blockIdx.x % per_start;
     Cand centre;                                          // (block_argmin contains the barriers that also publish `sp`)
@@ -225,6 +225,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_zoom_kernel(const __gri
             p.cur[blockIdx.x * K + threadIdx.x] = c;
         }
         return;
+    }
+    if (p.only_flagged) {
+        load_padded(sp, p.spec, n, padshift);
+        __syncthreads();
     }
 
     const int row = local / (ZOOM_SPAN / K), ch = local % (ZOOM_SPAN / K);
