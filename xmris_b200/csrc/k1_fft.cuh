@@ -53,25 +53,29 @@ struct K1Params {
 
 // N >= 8192: one shared buffer per spectrum serves as TMA landing slot, exchange A and exchange B ("in-place B"), one
 // ring stage, so that two CTAs fit on an SM (2 x 68 KiB) instead of one (196 KiB with separate buffers).
-template <int N>
+// GROUPS == 2 (N >= 8192, TMA): ONE CTA per SM made of two independent 256-thread groups (named barriers) that share a
+// ring of GROUPS + 1 such buffers: the group that finishes tile q re-arms its buffer with tile q + 3, which the OTHER group
+// picks up after its own current tile -- every load has half a tile period to land, and both groups compute all the time
+// (two separate CTAs with one buffer each leave 8 warps computing whenever one of them waits for its load).
+template <int N, int GROUPS = 1>
 struct K1Smem {
     using C = FftCfg<N>;
     static constexpr bool INPLACE_B = (N >= 8192);
-    static constexpr int STAGES = INPLACE_B ? 1 : K1_STAGES;
+    static constexpr int STAGES = GROUPS > 1 ? GROUPS + 1 : (INPLACE_B ? 1 : K1_STAGES);
     static constexpr size_t SLOT = INPLACE_B ? (C::SIZE_B > C::N ? C::SIZE_B : C::N) : C::N;   // complex elements
     static constexpr size_t RING = size_t(STAGES) * C::SPB * SLOT * sizeof(float2);
     static constexpr size_t B = INPLACE_B ? 0 : size_t(C::SPB) * C::SIZE_B * sizeof(float2);
-    static constexpr size_t RED = size_t(C::SPB) * 32 * 8;  // per group: up to 32 warps x (float, int)
+    static constexpr size_t RED = size_t(C::SPB) * GROUPS * 32 * 8;  // per spectrum slot: up to 32 warps x (float, int)
     static constexpr size_t BAR = 64;
     static constexpr size_t TW1 = (C::R1 == 16 && C::R2 == 16) ? size_t(15 * 16) * sizeof(float2) : 0;   // stage-1 twiddle table
     static constexpr size_t TOTAL = RING + B + RED + BAR + TW1;
 };
 
-template <int N>
+template <int N, int GROUPS = 1>
 constexpr int k1_min_blocks() {
     // shared-memory limited residency on a 227 KB SM, capped at 2048 threads and at 3 CTAs
-    int by_smem = int((227u * 1024u) / (K1Smem<N>::TOTAL + 1024));
-    int by_thr = 2048 / FftCfg<N>::THREADS;
+    int by_smem = int((227u * 1024u) / (K1Smem<N, GROUPS>::TOTAL + 1024));
+    int by_thr = 2048 / (FftCfg<N>::THREADS * GROUPS);
     int m = by_smem < by_thr ? by_smem : by_thr;
     if (m > 2) m = 2;   // persistent per-thread twiddles / 32 points per thread want <= 128 registers at 256 threads
     return m < 1 ? 1 : m;
@@ -95,10 +99,13 @@ enum : int { K1_FAST_ON = 1, K1_FAST_STORE = 2, K1_FAST_STATS = 4, K1_FAST_PHASE
 // PRUNE (generic statistics-only launches with p.run_max2 set): branch and bound on the level-0 bound of k1_max.cuh,
 //            |X| <= sum_n |x_n w_n|, for ANY geometry (zero-filled input, N = 8192, table windows): a tile whose spectra
 //            all fall below the running global maximum skips its transform; survivors are transformed in full.
-template <int N, bool INVERSE, int WIN, bool TMA, int FAST = 0, bool PRUNE = false>
-__global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_kernel(const __grid_constant__ K1Params p) {
+template <int N, bool INVERSE, int WIN, bool TMA, int FAST = 0, bool PRUNE = false, int GROUPS = 1>
+__global__ void __launch_bounds__(FftCfg<N>::THREADS * GROUPS, k1_min_blocks<N, GROUPS>()) k1_kernel(const __grid_constant__ K1Params p) {
     static_assert(!PRUNE || (FAST == 0 && !INVERSE), "PRUNE is a variant of the generic forward statistics pass");
-    __shared__ float run_s[2];   // PRUNE: thread 0's sample of the running maximum, double buffered by iteration parity
+    using KS = K1Smem<N, GROUPS>;
+    constexpr bool GRP = GROUPS > 1;
+    static_assert(!GRP || (KS::INPLACE_B && TMA), "grouped CTAs: in-place exchange B, TMA loads");
+    __shared__ float run_s[2 * GROUPS];   // PRUNE: a group's thread 0 samples the running maximum, double buffered by iteration parity
     __shared__ float2 ph_tab[32];   // generic / PHDEV variants: ph_step[16] | ph_fold[16] (from p.ph_dev when given)
     using C = FftCfg<N>;
     constexpr bool F = (FAST != 0);
@@ -106,25 +113,40 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
     static_assert(FftCfg<N>::R0 >= ZF, "the zero-fill fast variants need a first radix >= the zero-fill factor");
     constexpr bool TW_PERSIST = (N <= 4096);
     constexpr int NTW = (C::R0 > 1) ? C::C0 * (C::R0 - 1) : 1;
-    constexpr bool TW1_TAB_ = (K1Smem<N>::TW1 != 0);
+    constexpr bool TW1_TAB_ = (KS::TW1 != 0);
     // Folded phase (fast store+phase variants): with the stored index m = k1 + R0*c + m0(d), m0(d) = (R0*R1*d + N/2) mod N,
     // the rotation exp(2 pi i (a + b*m)) factors into E1(k1) * E2(c) * step(d).  E1 rides on the persistent stage-0
     // twiddles, E2 on the shared stage-1 twiddle table (both are 1 at index 0, where no multiply exists), so the epilogue
     // is ONE complex multiply per point by a kernel-parameter constant instead of two.
     constexpr bool FOLD = F && ((FAST & K1_FAST_PHASE) != 0) && TW_PERSIST && TW1_TAB_ && C::R0 > 1;
-    constexpr bool IPB = K1Smem<N>::INPLACE_B;
-    constexpr int STAGES = K1Smem<N>::STAGES;
-    constexpr size_t SLOT = K1Smem<N>::SLOT;
+    constexpr bool IPB = KS::INPLACE_B;
+    constexpr int STAGES = KS::STAGES;
+    constexpr size_t SLOT = KS::SLOT;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2* ring = reinterpret_cast<float2*>(smem_raw);
-    float2* Bbuf = reinterpret_cast<float2*>(smem_raw + K1Smem<N>::RING);
-    float* red = reinterpret_cast<float*>(smem_raw + K1Smem<N>::RING + K1Smem<N>::B);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + K1Smem<N>::RING + K1Smem<N>::B + K1Smem<N>::RED);
-    constexpr bool TW1_TAB = (K1Smem<N>::TW1 != 0);
-    float2* tw1_tab = TW1_TAB ? reinterpret_cast<float2*>(smem_raw + K1Smem<N>::RING + K1Smem<N>::B + K1Smem<N>::RED + K1Smem<N>::BAR) : nullptr;
+    float2* Bbuf = reinterpret_cast<float2*>(smem_raw + KS::RING);
+    float* red = reinterpret_cast<float*>(smem_raw + KS::RING + KS::B);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + KS::RING + KS::B + KS::RED);
+    constexpr bool TW1_TAB = (KS::TW1 != 0);
+    float2* tw1_tab = TW1_TAB ? reinterpret_cast<float2*>(smem_raw + KS::RING + KS::B + KS::RED + KS::BAR) : nullptr;
 
-    const int tid = threadIdx.x;
+    const int grp = GRP ? int(threadIdx.x) / C::THREADS : 0;      // grouped CTAs: which of the independent groups
+    const int tid = GRP ? int(threadIdx.x) % C::THREADS : int(threadIdx.x);
+    // block barrier of one group (named barrier 1 + grp) -- the whole CTA when there is one group
+    auto bsync = [&]() {
+        if (GRP) asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(C::THREADS) : "memory");
+        else __syncthreads();
+    };
+    auto bsync_and = [&](bool pred) -> bool {
+        if (GRP) {
+            int r;
+            asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.and.pred q, %2, %3, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                         : "=r"(r) : "r"(int(pred)), "r"(1 + grp), "n"(C::THREADS) : "memory");
+            return r != 0;
+        }
+        return __syncthreads_and(pred) != 0;
+    };
     const int g = tid / C::T;     // spectrum slot within the tile
     const int t = tid % C::T;     // thread within the spectrum
     constexpr bool PHDEV = F && ((FAST & K1_FAST_PHDEV) != 0);
@@ -225,12 +247,12 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
         }
     }
     if (TMA) {
-        if (tid == 0) {
+        if (threadIdx.x == 0) {
             for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
             fence_mbar_init();
         }
         __syncthreads();
-        if (tid == 0) {
+        if (threadIdx.x == 0) {
             for (int s = 0; s < STAGES; ++s) {
                 const long long tile = blockIdx.x + (long long)s * gridDim.x;
                 if (tile < ntiles) issue(tile, s);
@@ -238,33 +260,34 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
         }
     }
 
-    int it = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    int it = grp;   // the CTA's tile sequence number: group `grp` takes it = grp, grp + GROUPS, ...
+    for (long long tile = blockIdx.x + (long long)grp * gridDim.x; tile < ntiles; tile += (long long)GROUPS * gridDim.x, it += GROUPS) {
         const int slot = it % STAGES;
         const long long spec = tile * C::SPB + g;
         const bool valid = spec < p.batch;
         float2* my_slot = ring + (size_t(slot) * C::SPB + g) * SLOT;
         float2* my_B = IPB ? my_slot : Bbuf + size_t(g) * C::SIZE_B;
 
-        if (PRUNE && tid == 0) run_s[it & 1] = *reinterpret_cast<volatile float*>(p.run_max2);
+        const int rs = grp * 2 + ((it / GROUPS) & 1);
+        if (PRUNE && tid == 0) run_s[rs] = *reinterpret_cast<volatile float*>(p.run_max2);
         if (TMA) {
             mbar_wait(&bars[slot], (it / STAGES) & 1);
         } else {
             // plain-load path (unaligned base or odd n_in): cooperative coalesced copy of the tile's rows
             const long long s0 = tile * C::SPB;
             const int nvalid = int((p.batch - s0) < C::SPB ? (p.batch - s0) : C::SPB);
-            __syncthreads();   // previous tile's readers of this slot are done
+            bsync();   // previous tile's readers of this slot are done
             for (int idx = tid; idx < nvalid * n_in; idx += C::THREADS) {
                 const int r = idx / n_in, k = idx - r * n_in;
                 ring[(size_t(slot) * C::SPB + r) * SLOT + k] = in_base[(s0 + r) * n_in + k];
             }
-            __syncthreads();
+            bsync();
         }
 
         // ---- stage 0: load (zero-fill + window), R0-point DFTs, in-place exchange A --------------------
         float2 v[C::E];
         stage0_load<C, WIN>(t, my_slot, (F || valid) ? n_in : 0, pad_left, in_shift, p.scale, p.win, wcol, p.win_rows, v);
-        if (need_load_barrier) __syncthreads();
+        if (need_load_barrier) bsync();
         if (PRUNE) {
             // level-0 bound on the windowed, zero-filled samples this thread already holds
             float l1 = 0.f;
@@ -275,16 +298,16 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
             for (int off = LANES0 / 2; off > 0; off >>= 1) l1 += __shfl_xor_sync(0xffffffffu, l1, off);
             if (C::T > 32) {
                 constexpr int WPG0 = C::T / 32;
-                float* rv = red + size_t(g) * 64;
+                float* rv = red + size_t(g + grp * C::SPB) * 64;
                 if ((t & 31) == 0) rv[t >> 5] = l1;
-                __syncthreads();
+                bsync();
                 l1 = rv[0];
 #pragma unroll
                 for (int w = 1; w < WPG0; ++w) l1 += rv[w];
             }
-            const bool skip_mine = !valid || (l1 * l1 * 1.0001f < run_s[it & 1]);
+            const bool skip_mine = !valid || (l1 * l1 * 1.0001f < run_s[rs]);
             // (the barrier also orders thread 0's write of run_s and every thread's reads of the landing slot)
-            if (__syncthreads_and(skip_mine)) {
+            if (bsync_and(skip_mine)) {
                 if (t == 0 && valid) p.absmax[spec] = 0.f;
                 if (TMA && tid == 0) {
                     const long long nt = tile + (long long)STAGES * gridDim.x;
@@ -297,16 +320,16 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
             }
         }
         stage0_store<C, INVERSE, TW_PERSIST, ZF>(t, my_slot, v, tw_persist, tw0_base);
-        __syncthreads();
+        bsync();
         // ---- stage 1: R1-point DFTs, exchange B ----------------------------------------------------------
         if (IPB) {
             stage1_load<C>(t, my_slot, v);
-            __syncthreads();                       // exchange B overwrites exchange A: every thread has its inputs
+            bsync();                       // exchange B overwrites exchange A: every thread has its inputs
             stage1_store<C, INVERSE, TW1_TAB>(t, my_B, v, tw1_base, tw1_tab);
         } else {
             stage1<C, INVERSE, TW1_TAB>(t, my_slot, my_B, tw1_base, tw1_tab);
         }
-        __syncthreads();
+        bsync();
         // separate buffers: the input slot is free again -> prefetch tile it+STAGES while stage 2 and the epilogue run
         if (!IPB && TMA && tid == 0) {
             const long long nt = tile + (long long)STAGES * gridDim.x;
@@ -318,7 +341,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
         // ---- stage 2: R2-point DFTs, results in registers ------------------------------------------------
         stage2<C, INVERSE>(t, my_B, v);
         if (IPB) {
-            __syncthreads();                       // the shared buffer is free once every thread holds its results
+            bsync();                       // the shared buffer is free once every thread holds its results
             if (TMA && tid == 0) {
                 const long long nt = tile + (long long)STAGES * gridDim.x;
                 if (nt < ntiles) {
@@ -362,10 +385,10 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, k1_min_blocks<N>()) k1_ker
                 }
             } else if (C::T > 32) {
                 constexpr int WPG = C::T / 32;
-                float* rv = red + size_t(g) * 64;
+                float* rv = red + size_t(g + grp * C::SPB) * 64;
                 int* ri = reinterpret_cast<int*>(rv) + 32;
                 if ((t & 31) == 0) { rv[t >> 5] = best; ri[t >> 5] = besti; }
-                __syncthreads();
+                bsync();
                 if (t == 0) {
                     for (int w = 1; w < WPG; ++w) amax_combine(best, besti, rv[w], ri[w]);
                 }

@@ -1,6 +1,7 @@
 // One instantiation set of K1 per transform length: compile with -DXMR_N=<N>.
 #include "k1_launch.cuh"
 #include "k1_max.cuh"
+#include <cstdlib>
 
 
 
@@ -10,11 +11,12 @@
 
 namespace xmr {
 
-template <int N, bool INVERSE, int WIN, bool TMA, int FAST = 0, bool PRUNE = false>
-static cudaError_t launch_one(const K1Params& p, int max_ctas, cudaStream_t st) {
+template <int N, bool INVERSE, int WIN, bool TMA, int FAST, bool PRUNE, int GROUPS>
+static cudaError_t launch_impl(const K1Params& p, int max_ctas, cudaStream_t st) {
     using C = FftCfg<N>;
-    auto kern = k1_kernel<N, INVERSE, WIN, TMA, FAST, PRUNE>;
-    constexpr size_t smem = K1Smem<N>::TOTAL;
+    auto kern = k1_kernel<N, INVERSE, WIN, TMA, FAST, PRUNE, GROUPS>;
+    constexpr size_t smem = K1Smem<N, GROUPS>::TOTAL;
+    constexpr int threads = C::THREADS * GROUPS;
     static thread_local int cached_dev = -1;
     static thread_local int ctas_per_wave = 0;
     int dev = 0;
@@ -24,7 +26,7 @@ static cudaError_t launch_one(const K1Params& p, int max_ctas, cudaStream_t st) 
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) return e;
         int per_sm = 0, sms = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
         if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
@@ -36,8 +38,22 @@ static cudaError_t launch_one(const K1Params& p, int max_ctas, cudaStream_t st) 
     long long grid = ntiles < ctas_per_wave ? ntiles : ctas_per_wave;
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     if (grid < 1) return cudaSuccess;
-    kern<<<dim3((unsigned)grid), dim3(C::THREADS), smem, st>>>(p);
+    kern<<<dim3((unsigned)grid), dim3(threads), smem, st>>>(p);
     return cudaGetLastError();
+}
+
+template <int N, bool INVERSE, int WIN, bool TMA, int FAST = 0, bool PRUNE = false>
+static cudaError_t launch_one(const K1Params& p, int max_ctas, cudaStream_t st) {
+    // (input a quarter of the transform: nothing to prefetch, and two separate CTAs drift into opposite phases -- measured faster)
+    if constexpr (N >= 8192 && TMA && (FAST & K1_FAST_ZF4) == 0) {
+        // two 256-thread groups per CTA sharing a three-buffer ring (K1Smem); XMR_K1_GROUPS=1 selects the two-CTA form
+        static const bool grouped = !(getenv("XMR_K1_GROUPS") != nullptr && getenv("XMR_K1_GROUPS")[0] == '1');
+        if (grouped) {
+            // (ntiles here counts spectra: SPB == 1; one CTA takes two tiles at a time)
+            return launch_impl<N, INVERSE, WIN, TMA, FAST, PRUNE, 2>(p, max_ctas > 0 ? (max_ctas + 1) / 2 : 0, st);
+        }
+    }
+    return launch_impl<N, INVERSE, WIN, TMA, FAST, PRUNE, 1>(p, max_ctas, st);
 }
 
 #if XMR_N >= 512 && XMR_N <= 4096
