@@ -204,14 +204,16 @@ def _pruned_vs_plain(dev, fid_np, window, n_out=None, pad_left=0):
     pruned, plain = pruned.cpu().numpy(), plain.cpu().numpy()
     kept = pruned > 0
     assert ip == iq, "branch and bound changed the winning row"
-    assert vp == vq
+    # (N = 8192: both kernels form the stage-0 twiddles by a float32 power chain, contracted differently by the compiler --
+    #  the same maximum to an ulp; up to 4096 points the twiddles are table values and the maxima identical bit for bit)
+    assert vp == vq or (n >= 8192 and abs(vp - vq) <= 3e-7 * vq)
     assert np.allclose(pruned[kept], plain[kept], rtol=1e-6, atol=0)
     assert np.all(plain[~kept] <= vq)                       # pruned rows could not have won
     assert abs(float(running.item()) ** 0.5 - vq) <= 1e-6 * max(vq, 1e-30)
     return kept.mean()
 
 
-@pytest.mark.parametrize("n", [512, 1024, 2048, 4096])
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096, 8192])
 def test_pruned_statistics_pick_the_exact_winner(dev, n):
     from xmris_b200.synth import make_fids_numpy
 
@@ -242,7 +244,7 @@ def test_pruned_statistics_pick_the_exact_winner(dev, n):
 
 @pytest.mark.parametrize("n_in,n_out,pad_left,table", [(2048, 4096, 0, False), (1024, 4096, 0, False), (256, 512, 0, False),
                                                        (256, 1024, 0, False), (512, 2048, 0, False), (128, 512, 0, False),
-                                                       (4096, 8192, 0, False), (8192, 8192, 0, False), (1024, 2048, 0, False),
+                                                       (4096, 8192, 0, False), (8192, 8192, 0, False), (2048, 8192, 0, False), (1024, 2048, 0, False),
                                                        (1024, 4096, 1536, False), (2048, 2048, 0, True), (100, 256, 0, False),
                                                        (64, 64, 0, False), (1000, 4096, 7, True)])
 def test_pruned_statistics_any_geometry(dev, n_in, n_out, pad_left, table):

@@ -56,7 +56,7 @@ static cudaError_t launch_one(const K1Params& p, int max_ctas, cudaStream_t st) 
     return launch_impl<N, INVERSE, WIN, TMA, FAST, PRUNE, 1>(p, max_ctas, st);
 }
 
-#if XMR_N >= 512 && XMR_N <= 4096
+#if XMR_N >= 512
 template <int ZF>
 struct K1MaxPick {
     static constexpr auto kern = k1_max_zf_kernel<XMR_N, ZF>;
@@ -122,7 +122,7 @@ cudaError_t XMR_CAT(k1_launch_, XMR_N)(const K1Params& p, bool inverse, int win,
                 return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE | K1_FAST_PHASE | K1_FAST_PHDEV>(p, max_ctas, st);
             return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STORE | K1_FAST_PHASE>(p, max_ctas, st);
         }
-#if XMR_N >= 512 && XMR_N <= 4096
+#if XMR_N >= 512
         constexpr bool HAS_MAX_KERNEL = true;
 #else
         constexpr bool HAS_MAX_KERNEL = false;
@@ -130,13 +130,13 @@ cudaError_t XMR_CAT(k1_launch_, XMR_N)(const K1Params& p, bool inverse, int win,
         if (!st_ && stats && (p.run_max2 == nullptr || HAS_MAX_KERNEL)) {
             cudaError_t e = cudaMemsetAsync(p.absmax, 0, sizeof(float) * size_t(p.batch), st);   // atomicMax accumulators
             if (e != cudaSuccess) return e;
-#if XMR_N >= 512 && XMR_N <= 4096
+#if XMR_N >= 512
             if (p.run_max2 != nullptr) return launch_max(p, st);
 #endif
             return launch_one<XMR_N, false, 2, true, K1_FAST_ON | K1_FAST_STATS>(p, max_ctas, st);
         }
     }
-#if XMR_N >= 512 && XMR_N <= 4096
+#if XMR_N >= 512
     // the same geometry, statistics only with a running maximum: the branch-and-bound kernel on the short rows
     if (tma && win == 2 && p.pad_left == 0 && p.in_shift == 0 && p.out_shift == XMR_N / 2 && p.out == nullptr &&
         p.absmax != nullptr && p.argmax == nullptr && p.run_max2 != nullptr && (2 * p.n_in == XMR_N || 4 * p.n_in == XMR_N)) {

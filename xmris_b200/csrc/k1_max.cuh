@@ -1,6 +1,6 @@
 // K1-max: pass 1 of autophase(mode="single") -- per-spectrum max |S| for the global argmax (phasing.py:229-231), with
 // branch and bound.  Specialised for full-length input or input zero-filled 2x / 4x at the end, separable window,
-// fftshift-free statistics, N in [512, 4096].
+// fftshift-free statistics, N in [512, 8192] (N = 8192: 32 points per thread, one CTA per SM, stage-0 twiddles from a power chain).
 //
 // Two upper bounds on every output of a spectrum, each far cheaper than finishing the transform:
 //   level 0 (no transform):                          |X| <= sum_n |x_n| |w_n|                      (triangle inequality)
@@ -38,10 +38,11 @@ struct K1MaxSmem {
 // ZF: the input holds N/ZF points and is zero-filled at the end (zero_fill's default geometry): only the first R0/ZF rows
 // of a stage-0 column are loaded, bounded and -- for survivors -- transformed (degenerate first butterfly layers).
 template <int N, int ZF = 1>
-__global__ void __launch_bounds__(FftCfg<N>::THREADS, 2) k1_max_kernel(const __grid_constant__ K1Params p) {
+__global__ void __launch_bounds__(FftCfg<N>::THREADS, (N >= 8192 ? 1 : 2)) k1_max_kernel(const __grid_constant__ K1Params p) {
     using C = FftCfg<N>;
     using SM = K1MaxSmem<N>;
-    static_assert(C::E == 16 && C::R1 == 16 && C::R2 == 16 && C::T >= 32, "k1_max_kernel: N in [512, 4096]");
+    static_assert((C::E == 16 || C::E == 32) && C::R1 == 16 && C::R2 == 16 && C::T >= 32, "k1_max_kernel: N in [512, 8192]");
+    constexpr bool TWP = (N <= 4096);    // persistent stage-0 twiddles (N = 8192: 31 of them do not fit beside 32 points)
     static_assert(ZF >= 1 && C::R0 >= ZF && (ZF & (ZF - 1)) == 0, "zero-fill factor: a power of two <= R0");
     constexpr int NR = C::R0 / ZF;       // non-zero rows of a stage-0 column
     constexpr int NTW = C::C0 * (C::R0 - 1);
@@ -58,9 +59,9 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, 2) k1_max_kernel(const __g
     const int tid = threadIdx.x, g = tid / C::T, t = tid % C::T;
     const long long ntiles = (p.batch + C::SPB - 1) / C::SPB;
 
-    float2 tw_persist[NTW];
+    float2 tw_persist[TWP ? NTW : 1];
     float2 tw0_base[C::C0 * 2], tw1_base[C::C1 * 2];
-    init_twiddles<C, false>(t, p.twN, tw_persist, tw0_base, tw1_base);
+    init_twiddles<C, false>(t, p.twN, TWP ? tw_persist : nullptr, tw0_base, tw1_base);
     float wcol[C::C0];
 #pragma unroll
     for (int j = 0; j < C::C0; ++j) wcol[j] = p.win ? p.win[t + C::T * j] : p.scale;
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, 2) k1_max_kernel(const __g
                 for (int j = 0; j < C::C0; ++j)
 #pragma unroll
                     for (int n1 = 0; n1 < NR; ++n1) v[j * C::R0 + n1] = cscale(v[j * C::R0 + n1], wcol[j] * p.win_rows[n1]);
-                stage0_compute<C, false, true, ZF>(t, v, tw_persist, tw0_base);
+                stage0_compute<C, false, TWP, ZF>(t, v, tw_persist, tw0_base);
                 stage0_write<C>(t, my_slot, v);
             }
             __syncthreads();
@@ -155,9 +156,17 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, 2) k1_max_kernel(const __g
                 stage1_load<C>(t, my_slot, v);
                 stage1_compute<C, false, true>(t, v, tw1_base, tw1_tab);
 #pragma unroll
-                for (int i = 0; i < C::E; ++i) mq = fmaxf(mq, v[i].x * v[i].x + v[i].y * v[i].y);
+                for (int j = 0; j < C::C1; ++j) {                                                      // this thread's k1 values
+                    float mj = 0.f;
 #pragma unroll
-                for (int off = 1; off < 16; off <<= 1) mq += __shfl_xor_sync(0xffffffffu, mq, off);   // sum over b
+                    for (int c = 0; c < C::R1; ++c) {
+                        const float2 z = v[j * C::R1 + c];
+                        mj = fmaxf(mj, z.x * z.x + z.y * z.y);
+                    }
+#pragma unroll
+                    for (int off = 1; off < 16; off <<= 1) mj += __shfl_xor_sync(0xffffffffu, mj, off);   // sum over b
+                    mq = fmaxf(mq, mj);
+                }
                 mq = fmaxf(mq, __shfl_xor_sync(0xffffffffu, mq, 16));                                  // max over k1
             }
             if ((t & 31) == 0) red1[g * 32 + (t >> 5)] = mq;
@@ -220,10 +229,11 @@ struct K1MaxZfSmem {
 };
 
 template <int N, int ZF>
-__global__ void __launch_bounds__(FftCfg<N>::THREADS, 2) k1_max_zf_kernel(const __grid_constant__ K1Params p) {
+__global__ void __launch_bounds__(FftCfg<N>::THREADS, (N >= 8192 ? 1 : 2)) k1_max_zf_kernel(const __grid_constant__ K1Params p) {
     using C = FftCfg<N>;
     using SM = K1MaxZfSmem<N, ZF>;
-    static_assert(C::E == 16 && C::R1 == 16 && C::R2 == 16 && C::T >= 32, "k1_max_zf_kernel: N in [512, 4096]");
+    static_assert((C::E == 16 || C::E == 32) && C::R1 == 16 && C::R2 == 16 && C::T >= 32, "k1_max_zf_kernel: N in [512, 8192]");
+    constexpr bool TWP = (N <= 4096);
     static_assert(ZF >= 2 && C::R0 >= ZF && (ZF & (ZF - 1)) == 0, "zero-fill factor: a power of two in [2, R0]");
     constexpr int NR = C::R0 / ZF;       // non-zero rows of a stage-0 column
     constexpr int NV = C::C0 * NR;       // samples per thread and tile
@@ -242,9 +252,9 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, 2) k1_max_zf_kernel(const 
     constexpr long long SPT = (long long)ZF * C::SPB;                 // spectra per super-tile
     const long long ntiles = (p.batch + SPT - 1) / SPT;
 
-    float2 tw_persist[NTW];
+    float2 tw_persist[TWP ? NTW : 1];
     float2 tw0_base[C::C0 * 2], tw1_base[C::C1 * 2];
-    init_twiddles<C, false>(t, p.twN, tw_persist, tw0_base, tw1_base);
+    init_twiddles<C, false>(t, p.twN, TWP ? tw_persist : nullptr, tw0_base, tw1_base);
     float wcol[C::C0];
 #pragma unroll
     for (int j = 0; j < C::C0; ++j) wcol[j] = p.win ? p.win[t + C::T * j] : p.scale;
@@ -336,7 +346,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, 2) k1_max_zf_kernel(const 
 #pragma unroll
                     for (int n1 = 0; n1 < C::R0; ++n1)
                         v[j * C::R0 + n1] = n1 < NR ? cscale(raw[b][j * NR + n1], wcol[j] * p.win_rows[n1]) : make_float2(0.f, 0.f);
-                stage0_compute<C, false, true, ZF>(t, v, tw_persist, tw0_base);
+                stage0_compute<C, false, TWP, ZF>(t, v, tw_persist, tw0_base);
                 stage0_write<C>(t, my_x, v);
             }
             __syncthreads();
@@ -345,9 +355,17 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS, 2) k1_max_zf_kernel(const 
                 stage1_load<C>(t, my_x, v);
                 stage1_compute<C, false, true>(t, v, tw1_base, tw1_tab);
 #pragma unroll
-                for (int i = 0; i < C::E; ++i) mq = fmaxf(mq, v[i].x * v[i].x + v[i].y * v[i].y);
+                for (int j = 0; j < C::C1; ++j) {                                                      // this thread's k1 values
+                    float mj = 0.f;
 #pragma unroll
-                for (int off = 1; off < 16; off <<= 1) mq += __shfl_xor_sync(0xffffffffu, mq, off);   // sum over b
+                    for (int c = 0; c < C::R1; ++c) {
+                        const float2 z = v[j * C::R1 + c];
+                        mj = fmaxf(mj, z.x * z.x + z.y * z.y);
+                    }
+#pragma unroll
+                    for (int off = 1; off < 16; off <<= 1) mj += __shfl_xor_sync(0xffffffffu, mj, off);   // sum over b
+                    mq = fmaxf(mq, mj);
+                }
                 mq = fmaxf(mq, __shfl_xor_sync(0xffffffffu, mq, 16));                                  // max over k1
             }
             if ((t & 31) == 0) red[g * 32 + (t >> 5)] = mq;
