@@ -89,6 +89,12 @@ int xmr_zero_fill_c64(const void* in_dev, void* out_dev, int64_t batch, int n_in
 int xmr_roll_rows_c64(const void* in_dev, void* out_dev, int64_t batch, int n, int shift, void* stream);
 int xmr_scale_rows_c64(const void* in_dev, void* out_dev, int64_t batch, int n, const float* w_dev, void* stream);
 int xmr_rotate_rows_c64(const void* in_dev, void* out_dev, int64_t batch, int n, const void* rot_dev, void* stream);
+/* The same with both rotations of the index folded in and strided input rows (the pre- / post-chirp steps of the chirp-z
+ * transform that serves lengths that are not powers of two, e.g. the 1972-point FIDs of bruker.py:84 after
+ * remove_digital_filter; to_spectrum's ifftshift / fftshift, fourier.py:31-32):
+ *   out[b, (j + out_shift) mod n] = in[b * in_stride + (j + in_shift) mod n] * rot_dev[j],   j < n <= in_stride        */
+int xmr_rotate_rows_shift_c64(const void* in_dev, int64_t in_stride, void* out_dev, int64_t batch, int n, const void* rot_dev,
+                              int in_shift, int out_shift, void* stream);
 
 /* Per-spectrum phase: out[b,m] = in[b,m] * exp(2*pi*i*(a_turns[b] + b_turns[b]*m)).  (phasing.py:56-73 per voxel) */
 int xmr_phase_each_c64(const void* in_dev, void* out_dev, int64_t batch, int n, const double* a_turns_dev,

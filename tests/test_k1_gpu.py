@@ -139,6 +139,17 @@ def test_elementwise_ops(dev):
     np.testing.assert_allclose(D.scale_rows(xd, w).cpu().numpy(), x * w.astype(np.float32), rtol=1e-6)
     rot = np.exp(1j * rng.uniform(-3, 3, 300))
     assert rel_l2(D.rotate_rows(xd, rot).cpu().numpy(), x * rot) < 1e-6
+    # the shifted / strided form (pre- and post-chirp of the chirp-z path): out[(j + so) % n] = in[b, (j + si) % n] * rot[j]
+    from xmris_b200 import _lib
+    lib = _lib.load()
+    n = 211                                                     # rows of 300 points, the first 211 of each are used
+    rd = torch.from_numpy(rot[:n].astype(np.complex64)).to(dev)
+    for si, so in [(0, 0), (5, 0), (0, 105), (17, 200), (-3, -4)]:
+        od = torch.empty((13, n), dtype=torch.complex64, device=dev)
+        _lib.check(lib.xmr_rotate_rows_shift_c64(xd.data_ptr(), 300, od.data_ptr(), 13, n, rd.data_ptr(), si, so, None))
+        want = np.roll(np.roll(x[:, :n], -si, axis=1) * rot[:n].astype(np.complex64), so, axis=1)
+        assert rel_l2(od.cpu().numpy(), want) < 1e-6, (si, so)
+    assert lib.xmr_rotate_rows_shift_c64(xd.data_ptr(), 100, xd.data_ptr(), 13, n, rd.data_ptr(), 0, 0, None) != 0   # stride < n
     a = torch.from_numpy(rng.uniform(-1, 1, 13)).to(dev)
     b = torch.from_numpy(rng.uniform(-0.01, 0.01, 13)).to(dev)
     got = D.phase_each(xd, a, b).cpu().numpy()

@@ -40,6 +40,7 @@ SIGNATURES = {
     "xmr_roll_rows_c64": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "xmr_scale_rows_c64": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
     "xmr_rotate_rows_c64": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
+    "xmr_rotate_rows_shift_c64": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _i, _i, _vp]),
     "xmr_phase_each_c64": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "xmr_global_argmax": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
     "xmr_row_absmax_c64": (_i, [_vp, _i64, _i, _vp, _vp, _vp]),

@@ -114,6 +114,21 @@ __global__ void rotate_rows_kernel(const float2* __restrict__ in, float2* __rest
         out[i] = xmr::cmul(in[i], rot[i % n]);
     }
 }
+// out[b, (j + out_shift) mod n] = in[b * in_stride + (j + in_shift) mod n] * rot[j]: the pre- and post-chirp of the chirp-z
+// transform with the input rotation / fftshift folded in and the input rows taken out of longer ones
+__global__ void rotate_rows_shift_kernel(const float2* __restrict__ in, long long in_stride, float2* __restrict__ out,
+                                         long long batch, int n, const float2* __restrict__ rot, int in_shift, int out_shift) {
+    const long long total = batch * n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / n;
+        const int j = int(i - b * n);
+        int js = j + in_shift, jd = j + out_shift;
+        js -= js >= n ? n : 0;
+        jd -= jd >= n ? n : 0;
+        out[b * n + jd] = xmr::cmul(in[b * in_stride + js], rot[j]);
+    }
+}
 // one block per spectrum row chunk; phase in turns reduced in double once per (row, 64-point anchor)
 __global__ void phase_each_kernel(const float2* __restrict__ in, float2* __restrict__ out, long long batch, int n,
                                   const double* __restrict__ a_turns, const double* __restrict__ b_turns) {
@@ -396,6 +411,21 @@ int xmr_rotate_rows_c64(const void* in_dev, void* out_dev, int64_t batch, int n,
         static_cast<const float2*>(in_dev), static_cast<float2*>(out_dev), batch, n, static_cast<const float2*>(rot_dev));
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? XMR_OK : cuda_fail(e, "rotate_rows launch");
+}
+
+int xmr_rotate_rows_shift_c64(const void* in_dev, int64_t in_stride, void* out_dev, int64_t batch, int n, const void* rot_dev,
+                              int in_shift, int out_shift, void* stream) {
+    if (batch < 0 || n < 0 || in_stride < n) return fail(XMR_ERR_BAD_ARG, "bad sizes");
+    if (batch == 0 || n == 0) return XMR_OK;
+    if (!in_dev || !out_dev || !rot_dev) return fail(XMR_ERR_BAD_ARG, "NULL pointer");
+    if (in_dev == out_dev && (in_shift != out_shift || in_stride != n)) return fail(XMR_ERR_BAD_ARG, "in place only without a shift");
+    in_shift = ((in_shift % n) + n) % n;
+    out_shift = ((out_shift % n) + n) % n;
+    rotate_rows_shift_kernel<<<grid_for(batch * n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float2*>(in_dev), in_stride, static_cast<float2*>(out_dev), batch, n,
+        static_cast<const float2*>(rot_dev), in_shift, out_shift);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? XMR_OK : cuda_fail(e, "rotate_rows_shift launch");
 }
 
 int xmr_phase_each_c64(const void* in_dev, void* out_dev, int64_t batch, int n, const double* a_turns_dev,

@@ -77,33 +77,45 @@ def _bluestein_plan(n: int, inverse: bool, device):
         b = np.zeros(m, dtype=np.complex128)
         b[:n] = np.conj(chirp)
         b[m - n + 1:] = np.conj(chirp[1:][::-1])
-        filt = np.fft.fft(b)                                          # applied between the two power-of-two FFTs
-        plan = dict(m=m, chirp=chirp, filt_dev=torch.from_numpy(filt.astype(np.complex64)).to(device))
+        # the filter's spectrum (applied between the two power-of-two FFTs) comes from K1 as well: no host FFT on the path
+        b_dev = torch.from_numpy(b.astype(np.complex64)).to(device).reshape(1, m)
+        filt_dev, _, _ = fid_to_spectrum(b_dev, n_out=m, scale=1.0, out_shift=0)
+        plan = dict(m=m, chirp=chirp, filt_dev=filt_dev.reshape(m).contiguous(),
+                    chirp_dev=torch.from_numpy(chirp.astype(np.complex64)).to(device))
         _bluestein_tables[key] = plan
     return plan
 
 
 def _fft_any_length(fid, n_out, pad_left, window, scale, inverse, in_shift, out_shift, stream=None):
     """DFT of arbitrary length n_out <= BLUESTEIN_MAX_N (e.g. the 1972-point Bruker FIDs): chirp-z over K1's
-    power-of-two transforms.  Five launches (pre-chirp, FFT_M, filter, IFFT_M, post-chirp); not a fused fast path."""
+    power-of-two transforms.  Five launches of the library's own kernels (pre-chirp with the input rotation folded in, FFT_M,
+    filter, IFFT_M, post-chirp with the fftshift folded in, reading the first n_out points of the M-point rows in place);
+    not a fused fast path."""
     torch = _torch()
+    lib = _lib.load()
     n_in = fid.shape[-1]
     batch_shape = tuple(fid.shape[:-1])
     flat = fid.reshape(-1, n_in)
+    if not flat.is_contiguous():
+        flat = flat.contiguous()
+    batch = flat.shape[0]
     plan = _bluestein_plan(n_out, inverse, fid.device)
     m, chirp = plan["m"], plan["chirp"]
-    if in_shift:
-        flat = torch.roll(flat, -int(in_shift), dims=1).contiguous()      # x[k] <- fid[(k + in_shift) mod n]
     w = np.full(n_out, 1.0 if scale is None else float(scale)) if window is None else np.asarray(window, dtype=np.float64)
-    pre = (w * chirp)[pad_left:pad_left + n_in]
-    y = rotate_rows(flat, pre, stream=stream)
+    pre = torch.from_numpy(np.ascontiguousarray((w * chirp)[pad_left:pad_left + n_in].astype(np.complex64))).to(fid.device)
+    y = torch.empty_like(flat)
+    out = torch.empty((batch, n_out), dtype=flat.dtype, device=flat.device)
+    with torch.cuda.device(fid.device):
+        # y[k] = fid[(k + in_shift) mod n_in] * (w c)[pad_left + k]
+        _lib.check(lib.xmr_rotate_rows_shift_c64(_ptr(flat), n_in, _ptr(y), batch, n_in, _ptr(pre), int(in_shift) % max(n_in, 1),
+                                                 0, _stream_ptr(stream)))
     big, _, _ = fid_to_spectrum(y, n_out=m, pad_left=int(pad_left), scale=1.0, out_shift=0, stream=stream)
     big = _rotate_rows_dev(big, plan["filt_dev"], stream)
     conv, _, _ = fid_to_spectrum(big, inverse=True, scale=1.0 / m, in_shift=0, out_shift=0, stream=stream)
-    head = conv[:, :n_out].contiguous()
-    out = rotate_rows(head, chirp, stream=stream)
-    if out_shift:
-        out = torch.roll(out, int(out_shift), dims=1).contiguous()        # bin j -> (j + out_shift) mod n
+    with torch.cuda.device(fid.device):
+        # out[(j + out_shift) mod n_out] = conv[b, j] * c_j,  j < n_out  (rows of conv are m points long)
+        _lib.check(lib.xmr_rotate_rows_shift_c64(_ptr(conv), m, _ptr(out), batch, n_out, _ptr(plan["chirp_dev"]), 0,
+                                                 int(out_shift) % max(n_out, 1), _stream_ptr(stream)))
     return out.reshape(batch_shape + (n_out,))
 
 
