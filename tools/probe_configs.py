@@ -6,8 +6,8 @@ from xmris_b200 import chain, pervoxel
 from xmris_b200.synth import make_fids_torch
 
 dev = torch.device("cuda:0")
-def timeit(fn, iters=3):
-    fn(); torch.cuda.synchronize()
+def timeit(fn, iters=5):
+    fn(); fn(); fn(); torch.cuda.synchronize()     # (eager call, graph capture, first replay)
     ts = []
     for _ in range(iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -113,12 +113,18 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS * GROUPS, k1_min_blocks<N, 
     static_assert(FftCfg<N>::R0 >= ZF, "the zero-fill fast variants need a first radix >= the zero-fill factor");
     constexpr bool TW_PERSIST = (N <= 4096);
     constexpr int NTW = (C::R0 > 1) ? C::C0 * (C::R0 - 1) : 1;
-    constexpr bool TW1_TAB_ = (KS::TW1 != 0);
+    // Stage-1 twiddles W_M^(b*c) from a shared table (15 loads per 16-point butterfly) or from a power chain (14 multiplies):
+    // up to 4096 points the FFT is issue-bound and the LSU has headroom; at N = 8192 the shared-memory instruction queue is the
+    // first stall reason (profiles/k1_8192_full_r2.md) and the chain is faster -- except in the zero-filled store+phase variants
+    // (fewer stage-0 loads), where the table carries the folded phase and saves a complex multiply per point in the epilogue
+    // (measured, chain at 131072 spectra: 4096 -> 8192 3.83 ms with the table / 3.95 without; 8192 -> 8192 4.79 / 4.54).
+    constexpr bool TW1_TAB_ = (KS::TW1 != 0) && (N < 8192 || (F && (FAST & K1_FAST_PHASE) != 0 && ZF > 1));
     // Folded phase (fast store+phase variants): with the stored index m = k1 + R0*c + m0(d), m0(d) = (R0*R1*d + N/2) mod N,
     // the rotation exp(2 pi i (a + b*m)) factors into E1(k1) * E2(c) * step(d).  E1 rides on the persistent stage-0
-    // twiddles, E2 on the shared stage-1 twiddle table (both are 1 at index 0, where no multiply exists), so the epilogue
-    // is ONE complex multiply per point by a kernel-parameter constant instead of two.
-    constexpr bool FOLD = F && ((FAST & K1_FAST_PHASE) != 0) && TW_PERSIST && TW1_TAB_ && C::R0 > 1;
+    // twiddles (N = 8192: on the two bases W^n2, W^(4 n2) of their power chain w[k] = w1^(k&3) * w4^(k>>2), which then carries
+    // E1(k) = E1(1)^k), E2 on the shared stage-1 twiddle table (both are 1 at index 0, where no multiply exists), so the
+    // epilogue is ONE complex multiply per point by a kernel-parameter constant instead of two.
+    constexpr bool FOLD = F && ((FAST & K1_FAST_PHASE) != 0) && TW1_TAB_ && C::R0 > 1;
     constexpr bool IPB = KS::INPLACE_B;
     constexpr int STAGES = KS::STAGES;
     constexpr size_t SLOT = KS::SLOT;
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS * GROUPS, k1_min_blocks<N, 
     float2* Bbuf = reinterpret_cast<float2*>(smem_raw + KS::RING);
     float* red = reinterpret_cast<float*>(smem_raw + KS::RING + KS::B);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + KS::RING + KS::B + KS::RED);
-    constexpr bool TW1_TAB = (KS::TW1 != 0);
+    constexpr bool TW1_TAB = TW1_TAB_;
     float2* tw1_tab = TW1_TAB ? reinterpret_cast<float2*>(smem_raw + KS::RING + KS::B + KS::RED + KS::BAR) : nullptr;
 
     const int grp = GRP ? int(threadIdx.x) / C::THREADS : 0;      // grouped CTAs: which of the independent groups
@@ -193,9 +199,10 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS * GROUPS, k1_min_blocks<N, 
             turns -= floor(turns);
             double s, c;
             sincospi(2.0 * turns, &s, &c);
+            if (!TW_PERSIST && k1 != 1 && k1 != 4) continue;     // power chain: only its two bases carry the phase
 #pragma unroll
             for (int j = 0; j < C::C0; ++j) {
-                float2& w = tw_persist[(TW_PERSIST ? j * (C::R0 - 1) + k1 - 1 : 0)];
+                float2& w = TW_PERSIST ? tw_persist[(TW_PERSIST ? j * (C::R0 - 1) + k1 - 1 : 0)] : tw0_base[2 * j + (k1 == 4 ? 1 : 0)];
                 const double wr = double(w.x) * c - double(w.y) * s, wi = double(w.x) * s + double(w.y) * c;
                 w = make_float2(float(wr), float(wi));
             }
