@@ -223,17 +223,23 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS * GROUPS, k1_min_blocks<N, 
         }
     }
 
-    auto issue = [&](long long tile, int slot) {
+    // Barriers: one per ring slot -- and per consuming group in grouped CTAs (tile `it` uses barrier it % NBAR, slot it % STAGES;
+    // GROUPS and STAGES are coprime): every barrier is then waited on by ONE group in phase order, so the 1-bit phase parity
+    // can never alias (with one barrier per slot the other group's tile sits between two of mine: a group running two
+    // phases ahead of a late load would see "its" parity already flipped).
+    constexpr int NBAR = GRP ? GROUPS * STAGES : STAGES;
+    static_assert(!GRP || (STAGES % GROUPS != 0 && NBAR * 8 <= int(KS::BAR)), "grouped CTAs: coprime ring / group counts");
+    auto issue = [&](long long tile, int slot, int bar) {
         // producer: arm the barrier with the tile's byte count, then one bulk copy per spectrum row
         const long long s0 = tile * C::SPB;
         const int nvalid = int((p.batch - s0) < C::SPB ? (p.batch - s0) : C::SPB);
         const uint32_t row_bytes = uint32_t(n_in) * 8u;
-        mbar_arrive_expect_tx(&bars[slot], row_bytes * nvalid);
+        mbar_arrive_expect_tx(&bars[bar], row_bytes * nvalid);
         float2* dst = ring + size_t(slot) * C::SPB * SLOT;
         if (n_in == C::N && SLOT == size_t(C::N)) {
-            bulk_g2s(dst, in_base + s0 * n_in, row_bytes * nvalid, &bars[slot]);
+            bulk_g2s(dst, in_base + s0 * n_in, row_bytes * nvalid, &bars[bar]);
         } else {
-            for (int r = 0; r < nvalid; ++r) bulk_g2s(dst + size_t(r) * SLOT, in_base + (s0 + r) * n_in, row_bytes, &bars[slot]);
+            for (int r = 0; r < nvalid; ++r) bulk_g2s(dst + size_t(r) * SLOT, in_base + (s0 + r) * n_in, row_bytes, &bars[bar]);
         }
     };
 
@@ -255,14 +261,14 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS * GROUPS, k1_min_blocks<N, 
     }
     if (TMA) {
         if (threadIdx.x == 0) {
-            for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+            for (int s = 0; s < NBAR; ++s) mbar_init(&bars[s], 1);
             fence_mbar_init();
         }
         __syncthreads();
         if (threadIdx.x == 0) {
             for (int s = 0; s < STAGES; ++s) {
                 const long long tile = blockIdx.x + (long long)s * gridDim.x;
-                if (tile < ntiles) issue(tile, s);
+                if (tile < ntiles) issue(tile, s, s);
             }
         }
     }
@@ -278,7 +284,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS * GROUPS, k1_min_blocks<N, 
         const int rs = grp * 2 + ((it / GROUPS) & 1);
         if (PRUNE && tid == 0) run_s[rs] = *reinterpret_cast<volatile float*>(p.run_max2);
         if (TMA) {
-            mbar_wait(&bars[slot], (it / STAGES) & 1);
+            mbar_wait(&bars[it % NBAR], (it / NBAR) & 1);
         } else {
             // plain-load path (unaligned base or odd n_in): cooperative coalesced copy of the tile's rows
             const long long s0 = tile * C::SPB;
@@ -320,7 +326,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS * GROUPS, k1_min_blocks<N, 
                     const long long nt = tile + (long long)STAGES * gridDim.x;
                     if (nt < ntiles) {
                         fence_proxy_async_smem();
-                        issue(nt, slot);
+                        issue(nt, slot, (it + STAGES) % NBAR);
                     }
                 }
                 continue;
@@ -342,7 +348,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS * GROUPS, k1_min_blocks<N, 
             const long long nt = tile + (long long)STAGES * gridDim.x;
             if (nt < ntiles) {
                 fence_proxy_async_smem();
-                issue(nt, slot);
+                issue(nt, slot, (it + STAGES) % NBAR);
             }
         }
         // ---- stage 2: R2-point DFTs, results in registers ------------------------------------------------
@@ -353,7 +359,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS * GROUPS, k1_min_blocks<N, 
                 const long long nt = tile + (long long)STAGES * gridDim.x;
                 if (nt < ntiles) {
                     fence_proxy_async_smem();
-                    issue(nt, slot);
+                    issue(nt, slot, (it + STAGES) % NBAR);
                 }
             }
         }
