@@ -179,6 +179,75 @@ __device__ __forceinline__ void lane_grad(const float2* sp, int padshift, int m0
     }
 }
 
+// The same walk for K parameter sets at once (REANCHOR = 0): the K dependent chains (phasor recurrence, previous-point
+// differences) interleave in one loop and every point is loaded once.  Per set the arithmetic is lane_grad's, operation for
+// operation -- the polish evaluates x, x + (h0, 0), x + (0, h1) per iteration and is bound by the latency of these short chains.
+template <typename R, int K>
+__device__ __forceinline__ void lane_grad_multi(const float2* sp, int padshift, int m0, int m1, int n, const R (&turns0)[K],
+                                                const R (&tpu)[K], R u0, R du, int frozen, GradSums<R> (&a)[K]) {
+    if (m0 >= m1) return;
+    using O = RealOps<R>;
+    R sr[K], cr[K], si[K], ci[K], dp[K], qp[K], uqp[K];
+    R u = u0 + du * R(m0);
+    {
+        const float2 S = sp[m0 + (m0 >> padshift)];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            R t = turns0[k] + tpu[k] * u;
+            t -= floor(t);
+            O::sincospi2(t, &sr[k], &cr[k]);
+            R ti = tpu[k] * du;
+            ti -= floor(ti);
+            O::sincospi2(ti, &si[k], &ci[k]);
+            dp[k] = R(S.x) * cr[k] - R(S.y) * sr[k];
+            qp[k] = R(S.x) * sr[k] + R(S.y) * cr[k];
+            uqp[k] = u * qp[k];
+            const R neg = O::mn(dp[k], R(0));
+            a[k].P += neg * neg;
+            const R nq = neg * qp[k];
+            a[k].gP0 += nq;
+            a[k].gP1 += nq * u;
+            if (frozen < 0 ? (dp[k] > a[k].dmax) : (m0 == frozen)) { a[k].dmax = dp[k]; a[k].qmax = qp[k]; a[k].umax = u; }
+        }
+    }
+    const int mend = m1 < n ? m1 + 1 : m1;     // the point after the chunk only closes the last difference
+#pragma unroll 2
+    for (int m = m0 + 1; m < mend; ++m) {
+        u += du;
+        const float2 S = sp[m + (m >> padshift)];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const R ncr = cr[k] * ci[k] - sr[k] * si[k];
+            sr[k] = cr[k] * si[k] + sr[k] * ci[k];
+            cr[k] = ncr;
+            const R d = R(S.x) * cr[k] - R(S.y) * sr[k], q = R(S.x) * sr[k] + R(S.y) * cr[k];
+            const R uq = u * q;
+            const R D = d - dp[k], E = q - qp[k], F = uq - uqp[k];
+            const R ad = O::ab(D);
+            const bool nz = ad > O::tiny();
+            const R l = nz ? O::log2r(ad) : R(0);
+            const R sE = nz ? (D < R(0) ? -E : E) : R(0), sF = nz ? (D < R(0) ? -F : F) : R(0);
+            a[k].G2 += ad;
+            a[k].T2 += ad * l;
+            a[k].As0 += sE;
+            a[k].As1 += sF;
+            a[k].Al0 += l * sE;
+            a[k].Al1 += l * sF;
+            dp[k] = d;
+            qp[k] = q;
+            uqp[k] = uq;
+            if (m < m1) {
+                const R neg = O::mn(d, R(0));
+                a[k].P += neg * neg;
+                const R nq = neg * q;
+                a[k].gP0 += nq;
+                a[k].gP1 += nq * u;
+                if (frozen < 0 ? (d > a[k].dmax) : (m == frozen)) { a[k].dmax = d; a[k].qmax = q; a[k].umax = u; }
+            }
+        }
+    }
+}
+
 // ---- bounded Newton iteration on (p0, p1), thread-level state --------------------------------------------------------------
 // Every iteration needs the gradient at x and at x + (h0, 0), x + (0, h1): a secant Hessian at the scale h, which smooths the
 // objective's fine roughness (one kink per spectral point) instead of differentiating through it.

@@ -309,6 +309,8 @@ constexpr int POLISH_MAXIT = 8;
 
 struct PolishShared {
     double part[SEARCH_THREADS / 32][3][GRAD_NSUMS];
+    FG fg[3];                     // the three evaluation points' results (threads 0..2 -> thread 0)
+    double base[GRAD_NSUMS];      // the combined sums at the base point
     double y0, y1;        // trial point of this round
     double H, pen;        // entropy term and 1000 * penalty at the last accepted point
     int frozen;
@@ -322,34 +324,47 @@ __device__ __forceinline__ void polish_eval(const float2* sp, int padshift, int 
     const double y0 = sh.y0, y1 = sh.y1;
     const int frozen = sh.frozen;
     // per-point arithmetic in float32 (random 1e-7 relative errors average out over the sums; the anchor phase of every
-    // thread's short chunk is reduced in float64), cross-warp combination and everything after it in float64
-#pragma unroll 1
+    // thread's short chunk is reduced in float64), cross-warp combination and everything after it in float64.  The three
+    // points are walked in ONE interleaved loop (lane_grad_multi): the iteration is bound by the latency of these short
+    // dependent chains, not by their instruction count.
+    GradSums<float> a[3];
+    float t0f[3], tpuf[3];
+    const double um0 = u0 + du * double(m0);
+#pragma unroll
     for (int k = 0; k < 3; ++k) {
-        GradSums<float> a;
-        a.init();
+        a[k].init();
         const double q0 = y0 + (k == 1 ? NEWTON_H0 : 0.0), q1 = y1 + (k == 2 ? NEWTON_H1 : 0.0);
-        // fold the first-order phase at the chunk start into the zero-order term in float64: lane_grad's own float32
-        // reduction then only sees |turns| < 1 plus the small in-chunk ramp
-        const double um0 = u0 + du * double(m0);
+        // fold the first-order phase at the chunk start into the zero-order term in float64: the float32 reduction of the
+        // walk then only sees |turns| < 1 plus the small in-chunk ramp
         double t0 = q0 / 360.0 + (q1 / 360.0) * um0;
         t0 -= floor(t0);
-        lane_grad<float>(sp, padshift, m0, m1, n, float(t0), float(q1 / 360.0), float(-du * double(m0)), float(du), frozen, a);
+        t0f[k] = float(t0);
+        tpuf[k] = float(q1 / 360.0);
+    }
+    lane_grad_multi<float, 3>(sp, padshift, m0, m1, n, t0f, tpuf, float(-du * double(m0)), float(du), frozen, a);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
         // (u restarts at 0 inside the chunk: shift the u-weighted sums back to the global ramp)
-        a.gP1 += float(um0) * a.gP0;
-        a.As1 += float(um0) * a.As0;
-        a.Al1 += float(um0) * a.Al0;
-        a.umax += float(um0);
-        a.warp_reduce();
-        if (lane == 0) grad_store(a, sh.part[warp][k]);
+        a[k].gP1 += float(um0) * a[k].gP0;
+        a[k].As1 += float(um0) * a[k].As0;
+        a[k].Al1 += float(um0) * a[k].Al0;
+        a[k].umax += float(um0);
+        a[k].warp_reduce();
+        if (lane == 0) grad_store(a[k], sh.part[warp][k]);
     }
     __syncthreads();
+    // threads 0..2 combine the warps' partial sums of one point each; thread 0 then collects the three results
+    if (threadIdx.x < 3) {
+        const int k = threadIdx.x;
+        GradSums<double> tot = grad_load(sh.part[0][k]);
+        for (int w = 1; w < SEARCH_THREADS / 32; ++w) tot.merge(grad_load(sh.part[w][k]));
+        sh.fg[k] = acme_finish(tot, n);
+        if (k == 0) grad_store(tot, sh.base);
+    }
+    if (threadIdx.x < 32) __syncwarp();
     if (threadIdx.x == 0) {
-        for (int k = 0; k < 3; ++k) {
-            GradSums<double> tot = grad_load(sh.part[0][k]);
-            for (int w = 1; w < SEARCH_THREADS / 32; ++w) tot.merge(grad_load(sh.part[w][k]));
-            out[k] = acme_finish(tot, n);
-            if (k == 0 && base_sums) *base_sums = tot;
-        }
+        for (int k = 0; k < 3; ++k) out[k] = sh.fg[k];
+        if (base_sums) *base_sums = grad_load(sh.base);
     }
     __syncthreads();
 }
