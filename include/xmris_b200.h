@@ -189,6 +189,11 @@ typedef struct xmr_host_chain_desc {
 int xmr_chain_host_c64(const xmr_host_chain_desc* desc, const void* fid_host, void* out_host, int64_t batch,
                        double* result_host, double* p0_host, double* p1_host, int* pivot_host, float* fun_host);
 int xmr_host_workspace_release(void);
+/* mode 1 keeps the whole FID batch in device memory between its two passes when it fits; otherwise -- or when the batch
+ * exceeds `bytes` set here (0, the default: whatever is free) -- the FID chunks are uploaded twice (pass 1 over
+ * double-buffered chunks, the winning row fetched again, pass 2 over the re-uploaded chunks): data sets larger than HBM,
+ * and long-lived processes that must not hold gigabytes per thread.  Same results either way.                           */
+int xmr_host_chain_resident_limit(int64_t bytes);
 
 /* The mode="single" chain on DEVICE-resident data in one call (the reference's `.xmr.zero_fill().xmr.apodize_exp()
  * .xmr.to_spectrum().xmr.autophase()` on an array that already lives in HBM): branch-and-bound pass 1 -> global argmax

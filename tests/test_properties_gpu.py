@@ -177,6 +177,28 @@ def test_host_c_abi_chain_matches_device_chain(mode, n_in, zf):
     hostabi.release_workspace()
 
 
+@pytest.mark.parametrize("n_in,zf", [(1024, 2048), (4096, None)])
+def test_host_chain_streams_twice_when_the_fids_may_not_stay_resident(n_in, zf):
+    """mode="single" on a batch above the resident limit (a data set larger than HBM): pass 1 over double-buffered chunks,
+    the winning row fetched again, pass 2 over re-uploaded chunks -- bit-identical to the resident form."""
+    from xmris_b200 import hostabi
+
+    batch = 2500
+    fid, t = _fids("1H", batch, n_in, seed=35)
+    host = fid.cpu().numpy()
+    ap = dict(mode="single", peak_width=100)
+    ref, rfreqs, rinfo = hostabi.chain_host(host, t, zf, "end", 5.0, autophase=ap, chunk=300)
+    hostabi.release_workspace()
+    hostabi.set_resident_limit(1)
+    try:
+        out, freqs, info = hostabi.chain_host(host, t, zf, "end", 5.0, autophase=ap, chunk=300)
+    finally:
+        hostabi.set_resident_limit(0)
+        hostabi.release_workspace()
+    assert (info["p0"], info["p1"], info["pivot"]) == (rinfo["p0"], rinfo["p1"], rinfo["pivot"])
+    assert np.array_equal(out, ref)
+
+
 def test_device_chain_replays_a_cuda_graph_and_gives_the_same_result():
     import torch
 

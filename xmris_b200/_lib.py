@@ -63,6 +63,7 @@ SIGNATURES = {
 
     "xmr_chain_host_c64": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "xmr_host_workspace_release": (_i, []),
+    "xmr_host_chain_resident_limit": (_i, [_i64]),
 }
 
 

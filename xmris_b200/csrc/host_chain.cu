@@ -136,10 +136,17 @@ bool split_window(const double* w, int n, std::vector<float>& cols, std::vector<
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 std::atomic<long long> g_graph_launches{0};
+std::atomic<long long> g_resident_limit{0};    // xmr_host_chain_resident_limit: bytes of FIDs mode=single may keep on the device
 
 }  // namespace
 
 extern "C" {
+
+int xmr_host_chain_resident_limit(int64_t bytes) {
+    if (bytes < 0) return xmr_abi::fail(XMR_ERR_BAD_ARG, "resident limit must be >= 0 (0: whatever is free)");
+    g_resident_limit.store(bytes);
+    return XMR_OK;
+}
 
 int xmr_host_workspace_release(void) {
     Workspace& w = g_ws;
@@ -186,18 +193,20 @@ int xmr_chain_host_c64(const xmr_host_chain_desc* d, const void* fid_host, void*
     const size_t o_row = align_up(o_arg + 64, 256);                       // one spectrum + its stats
     const size_t o_sws = align_up(o_row + row_out + 64, 256);
     const size_t small = o_sws + size_t(xmr_autophase_workspace_bytes());
-    const bool keep_all_in = (d->autophase_mode == 1);                     // the FIDs are read twice
+    bool keep_all_in = (d->autophase_mode == 1);                           // the FIDs are read twice
     if (keep_all_in) {
-        // mode="single" keeps the whole FID batch on the device between its two passes: say so instead of failing inside
-        // cudaMalloc when it cannot fit (the workspace is cached per thread; xmr_host_workspace_release() returns it)
+        // mode="single" keeps the whole FID batch on the device between its two passes when it fits (and stays under the
+        // caller's limit, xmr_host_chain_resident_limit); a larger data set is streamed through twice instead -- pass 1 over
+        // double-buffered chunks, the winning row fetched again, pass 2 over the re-uploaded chunks
         size_t free_b = 0, total_b = 0;
         XMR_CU(cudaMemGetInfo(&free_b, &total_b));
         const size_t need = size_t(batch) * row_in + 2 * size_t(chunk) * row_out + small;
-        if (need > free_b + g_ws.d_in_bytes + 2 * g_ws.d_out_bytes + g_ws.d_small_bytes)
-            return xmr_abi::fail(XMR_ERR_BAD_ARG, "host chain (mode=single) needs %.1f GB of device memory for %lld FIDs, %.1f GB are free: "
-                                 "split the batch (the global |S| maximum then has to be taken over the parts by the caller) or use the "
-                                 "device-resident entry points", need / 1e9, (long long)batch, free_b / 1e9);
+        const long long limit = g_resident_limit.load();
+        if (need > free_b + g_ws.d_in_bytes + 2 * g_ws.d_out_bytes + g_ws.d_small_bytes ||
+            (limit > 0 && size_t(batch) * row_in > size_t(limit)))
+            keep_all_in = false;
     }
+    const bool restream = (d->autophase_mode == 1) && !keep_all_in;
     int rc = ensure_workspace(keep_all_in ? size_t(batch) * row_in : 2 * size_t(chunk) * row_in, size_t(chunk) * row_out, small);
     if (rc != XMR_OK) return rc;
     Workspace& w = g_ws;
@@ -281,12 +290,14 @@ int xmr_chain_host_c64(const xmr_host_chain_desc* d, const void* fid_host, void*
         // ---- pass 1 trails the uploads chunk by chunk ---------------------------------------------------------------
         for (int64_t c = 0; c < nchunks; ++c) {
             const int64_t lo = c * chunk, nb = std::min(chunk, batch - lo);
+            if (restream && c >= 2) XMR_CUC(cudaStreamWaitEvent(w.s_in, in_free[c % 2], 0));   // slot last read by chunk c-2
             XMR_CUC(cudaMemcpyAsync(d_in_chunk(c), h_in + size_t(lo) * row_in, size_t(nb) * row_in, cudaMemcpyHostToDevice, w.s_in));
             XMR_CUC(cudaEventRecord(in_done[c], w.s_in));
             XMR_CUC(cudaStreamWaitEvent(w.s_cmp, in_done[c], 0));
             // branch-and-bound statistics: the running maximum (one float at o_arg + 32) is shared by the chunks of this call
             XMR_RC(xmr_fid_absmax_pruned_c64(d_in_chunk(c), nb, n_in, n_out, d->pad_left, win_mode, win_dev, rows.data(), scale,
                                              absmax + lo, reinterpret_cast<float*>(sm + o_arg + 32), c == 0 ? 1 : 0, w.s_cmp));
+            if (restream) XMR_CUC(cudaEventRecord(in_free[c % 2], w.s_cmp));
         }
         // ---- winner, its spectrum, the search ------------------------------------------------------------------------
         unsigned char* arg = sm + o_arg;
@@ -300,7 +311,12 @@ int xmr_chain_host_c64(const xmr_host_chain_desc* d, const void* fid_host, void*
         unsigned char* rowbuf = sm + o_row;
         float* row_abs = reinterpret_cast<float*>(rowbuf + row_out);
         int* row_arg = reinterpret_cast<int*>(rowbuf + row_out + 16);
-        XMR_RC(xmr_fid_to_spectrum_c64(d_in + size_t(row) * row_in, rowbuf, 1, n_in, n_out, d->pad_left, win_mode, win_dev, rows.data(),
+        const unsigned char* row_dev = d_in + size_t(row) * row_in;
+        if (restream) {      // the winning FID is no longer on the device (s_cmp is idle here: both ring slots are free)
+            XMR_CUC(cudaMemcpyAsync(d_in, h_in + size_t(row) * row_in, row_in, cudaMemcpyHostToDevice, w.s_cmp));
+            row_dev = d_in;
+        }
+        XMR_RC(xmr_fid_to_spectrum_c64(row_dev, rowbuf, 1, n_in, n_out, d->pad_left, win_mode, win_dev, rows.data(),
                                        scale, 0, 0, n_out / 2, row_abs, row_arg, XMR_PHASE_NONE, 0.0, 0.0, w.s_cmp));
         int idx = 0;
         XMR_CUC(cudaMemcpyAsync(&idx, row_arg, 4, cudaMemcpyDeviceToHost, w.s_cmp));

@@ -90,3 +90,9 @@ def chain_host(fid, time_coord, target_points=None, position="end", lb=None, aut
 def release_workspace():
     """Free the calling thread's device workspace of the host chain."""
     _lib.check(_lib.load().xmr_host_workspace_release())
+
+
+def set_resident_limit(nbytes=0):
+    """``mode="single"`` keeps the FIDs on the device between its two passes only up to ``nbytes`` (0: whatever is free);
+    larger batches are uploaded twice, chunk by chunk -- data sets beyond HBM, or a bound on what a long-lived process holds."""
+    _lib.check(_lib.load().xmr_host_chain_resident_limit(int(nbytes)))
