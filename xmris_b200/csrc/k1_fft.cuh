@@ -113,18 +113,20 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS * GROUPS, k1_min_blocks<N, 
     static_assert(FftCfg<N>::R0 >= ZF, "the zero-fill fast variants need a first radix >= the zero-fill factor");
     constexpr bool TW_PERSIST = (N <= 4096);
     constexpr int NTW = (C::R0 > 1) ? C::C0 * (C::R0 - 1) : 1;
-    // Stage-1 twiddles W_M^(b*c) from a shared table (15 loads per 16-point butterfly) or from a power chain (14 multiplies):
-    // up to 4096 points the FFT is issue-bound and the LSU has headroom; at N = 8192 the shared-memory instruction queue is the
-    // first stall reason (profiles/k1_8192_full_r2.md) and the chain is faster -- except in the zero-filled store+phase variants
-    // (fewer stage-0 loads), where the table carries the folded phase and saves a complex multiply per point in the epilogue
-    // (measured, chain at 131072 spectra: 4096 -> 8192 3.83 ms with the table / 3.95 without; 8192 -> 8192 4.79 / 4.54).
-    constexpr bool TW1_TAB_ = (KS::TW1 != 0) && (N < 8192 || (F && (FAST & K1_FAST_PHASE) != 0 && ZF > 1));
+    // Stage-1 twiddles W_M^(b*c) from a shared table (15 loads per 16-point butterfly) or from a power chain (14 multiplies).
+    // Measured, alternating runs on one box (the mix also decides the SM clock under the power cap): the table wins for
+    // full-length input up to 4096 points (C5 pass 2: 11.4-11.5 ms against 11.5-11.7 ms); the chain wins at N = 8192, where the
+    // shared-memory instruction queue is the first stall reason (profiles/k1_8192_full_r2.md: 8192 -> 8192 0.84 -> 0.88 of the
+    // roofline), and in the zero-filled store+phase variants of every length (chain 2048 -> 4096: 3.32 -> 3.21 ms,
+    // 1024 -> 2048: 3.17 -> 3.08 ms, 512 -> 1024: 3.20 -> 3.12 ms).  The folded phase works with either (see FOLD).
+    constexpr bool TW1_TAB_ = (KS::TW1 != 0) && N < 8192 && !(F && (FAST & K1_FAST_PHASE) != 0 && ZF > 1);
     // Folded phase (fast store+phase variants): with the stored index m = k1 + R0*c + m0(d), m0(d) = (R0*R1*d + N/2) mod N,
     // the rotation exp(2 pi i (a + b*m)) factors into E1(k1) * E2(c) * step(d).  E1 rides on the persistent stage-0
     // twiddles (N = 8192: on the two bases W^n2, W^(4 n2) of their power chain w[k] = w1^(k&3) * w4^(k>>2), which then carries
     // E1(k) = E1(1)^k), E2 on the shared stage-1 twiddle table (both are 1 at index 0, where no multiply exists), so the
     // epilogue is ONE complex multiply per point by a kernel-parameter constant instead of two.
-    constexpr bool FOLD = F && ((FAST & K1_FAST_PHASE) != 0) && TW1_TAB_ && C::R0 > 1;
+    // Without the table E2 rides on the two bases of the stage-1 power chain in the same way.
+    constexpr bool FOLD = F && ((FAST & K1_FAST_PHASE) != 0) && C::R0 > 1 && C::R1 > 1;
     constexpr bool IPB = KS::INPLACE_B;
     constexpr int STAGES = KS::STAGES;
     constexpr size_t SLOT = KS::SLOT;
@@ -203,6 +205,22 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS * GROUPS, k1_min_blocks<N, 
 #pragma unroll
             for (int j = 0; j < C::C0; ++j) {
                 float2& w = TW_PERSIST ? tw_persist[(TW_PERSIST ? j * (C::R0 - 1) + k1 - 1 : 0)] : tw0_base[2 * j + (k1 == 4 ? 1 : 0)];
+                const double wr = double(w.x) * c - double(w.y) * s, wi = double(w.x) * s + double(w.y) * c;
+                w = make_float2(float(wr), float(wi));
+            }
+        }
+    }
+    if (FOLD && !TW1_TAB_) {
+        // stage-1 power chain w[c] = w1^(c&3) * w4^(c>>2): E2(c) = E2(1)^c rides on its bases (E2(4) computed exactly)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            double turns = ph_b_turns * double(C::R0 * (e == 0 ? 1 : 4));
+            turns -= floor(turns);
+            double s, c;
+            sincospi(2.0 * turns, &s, &c);
+#pragma unroll
+            for (int j = 0; j < C::C1; ++j) {
+                float2& w = tw1_base[2 * j + e];
                 const double wr = double(w.x) * c - double(w.y) * s, wi = double(w.x) * s + double(w.y) * c;
                 w = make_float2(float(wr), float(wi));
             }
