@@ -45,6 +45,37 @@ def test_plain_fft_all_lengths(dev, n_out):
         assert max(errs) < TOL, (n_out, batch, max(errs))
 
 
+@pytest.mark.parametrize("n_in", [8192, 4096, 2048, 1000])
+def test_grouped_ctas_at_8192_every_tail(dev, n_in):
+    """N = 8192 runs ONE CTA per SM made of two independent thread groups that share a three-buffer TMA ring: batches
+    below / at / just above one, two and three tiles per CTA (148 SMs), idle second groups, ragged tails; every row against
+    the oracle, with the statistics and the phase epilogues."""
+    import torch
+    from xmris_b200 import device as D
+
+    n_out = 8192
+    rng = np.random.default_rng(n_in)
+    t = np.arange(n_in) / 5000.0
+    _, t_pad, _ = orc.zero_fill(np.zeros(n_in), 0, t, n_out, "end")
+    w = np.exp(-np.pi * 3.0 * t_pad) / np.sqrt(n_out)
+    for batch in (1, 2, 147, 148, 149, 295, 296, 297, 445, 593):
+        x = _rand(rng, (batch, n_in))
+        ref, freqs = orc.chain_to_spectrum(x.astype(np.complex128), 1, t, n_out, "end", 3.0)
+        xd = torch.from_numpy(x).to(dev)
+        spec, amax, _ = D.fid_to_spectrum(xd, n_out=n_out, window=w, want_stats=True)
+        got = spec.cpu().numpy()
+        assert max(rel_l2(got[i], ref[i]) for i in range(batch)) < TOL, batch
+        np.testing.assert_allclose(amax.cpu().numpy(), np.abs(ref).max(axis=1), rtol=3e-5)
+        p0, p1, pivot = -33.0, 1234.5, float(freqs[n_out // 3])
+        refp, _ = orc.phase(ref, 1, freqs, p0, p1, pivot)
+        span = freqs.max() - freqs.min()
+        b = (p1 / 360.0) * (freqs[1] - freqs[0]) / span
+        a = p0 / 360.0 + (p1 / 360.0) * (freqs[0] - pivot) / span
+        specp, _, _ = D.fid_to_spectrum(xd, n_out=n_out, window=w, phase_turns=(a, b))
+        gotp = specp.cpu().numpy()
+        assert max(rel_l2(gotp[i], refp[i]) for i in range(batch)) < TOL, batch
+
+
 @pytest.mark.parametrize("n_in,n_out,position", [(1024, 2048, "end"), (4096, 8192, "end"), (64, 512, "end"),
                                                    (32, 128, "symmetric"), (1000, 4096, "symmetric"),
                                                    (1023, 2048, "end"), (37, 64, "symmetric"), (2048, 2048, "end")])
