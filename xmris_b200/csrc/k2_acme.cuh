@@ -43,7 +43,11 @@ template <int N>
 struct K2aSmem {
     using C = FftCfg<N>;
     static constexpr int PADSHIFT = ilog2(N / 32 > 0 ? N / 32 : 1);
-    static constexpr size_t SLOT = size_t(C::N) * sizeof(float2);
+    // N >= 8192: ONE buffer is TMA landing slot, both FFT exchanges (in place, as K1 does at this length) and then the padded
+    // spectrum the search walks: 92 KB per CTA instead of 156 KB, so that TWO CTAs fit on an SM (four instead of two warps per
+    // SM sub-partition for a latency-bound search); the next voxel's FID is fetched at the end of the voxel.
+    static constexpr bool IPB = (N >= 8192);
+    static constexpr size_t SLOT = IPB ? 0 : size_t(C::N) * sizeof(float2);
     static constexpr size_t SPN = (size_t(C::N) + (size_t(C::N) >> PADSHIFT) + 2);
     static constexpr size_t B = (C::SIZE_B > SPN ? size_t(C::SIZE_B) : SPN) * sizeof(float2);
     static constexpr size_t DEC = size_t(4) * K2A_GSTRIDE * sizeof(float2);     // block moments G_1, G_2, G_3, G_5
@@ -74,7 +78,7 @@ struct K2aShared {      // lives in the MISC area
 static_assert(sizeof(K2aShared) <= 12288, "K2aShared must fit the MISC area");
 
 template <int N>
-__global__ void __launch_bounds__(FftCfg<N>::T, (N >= 8192 ? 1 : (FftCfg<N>::T >= 256 ? 2 : (FftCfg<N>::T >= 128 ? 4 : 8))))
+__global__ void __launch_bounds__(FftCfg<N>::T, (FftCfg<N>::T >= 256 ? 2 : (FftCfg<N>::T >= 128 ? 4 : 8)))
 k2_acme_kernel(const __grid_constant__ K2Params p) {
     using C = FftCfg<N>;
     using SM = K2aSmem<N>;
@@ -87,8 +91,9 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
     static_assert(C::T >= 32 && N >= 512, "per-voxel kernel needs N >= 512");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2* slot = reinterpret_cast<float2*>(smem_raw);
+    constexpr bool IPB = SM::IPB;
     float2* Bbuf = reinterpret_cast<float2*>(smem_raw + SM::SLOT);
+    float2* slot = IPB ? Bbuf : reinterpret_cast<float2*>(smem_raw);
     float2* sp = Bbuf;                                                     // padded spectrum reuses exchange B
     float2* gdec = reinterpret_cast<float2*>(smem_raw + SM::SLOT + SM::B);
     float* rowf = reinterpret_cast<float*>(smem_raw + SM::SLOT + SM::B + SM::DEC);
@@ -148,9 +153,15 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
             if (need_load_barrier) __syncthreads();
             stage0_store<C, false, TW_PERSIST>(t, slot, v, tw_persist, tw0_base);
             __syncthreads();
-            stage1<C, false>(t, slot, Bbuf, tw1_base);
+            if (IPB) {
+                stage1_load<C>(t, slot, v);
+                __syncthreads();                               // exchange B overwrites exchange A
+                stage1_store<C, false>(t, Bbuf, v, tw1_base);
+            } else {
+                stage1<C, false>(t, slot, Bbuf, tw1_base);
+            }
             __syncthreads();
-            if (p.use_tma && t == 0) {
+            if (!IPB && p.use_tma && t == 0) {
                 const long long nv = vox + gridDim.x;
                 if (nv < p.batch) {
                     fence_proxy_async_smem();
@@ -192,6 +203,19 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
         } else {
             float best = -1.f;
             int besti = 0x7fffffff;
+            if (IPB) {
+                // the padded layout is written over the buffer the spectrum landed in: every thread reads its points first
+                float2 tmp[N / C::T];
+#pragma unroll
+                for (int i = 0; i < N / C::T; ++i) tmp[i] = slot[t + C::T * i];
+                __syncthreads();
+#pragma unroll
+                for (int i = 0; i < N / C::T; ++i) {
+                    const int m = t + C::T * i;
+                    sp[m + (m >> PADSHIFT)] = tmp[i];
+                    amax_combine(best, besti, tmp[i].x * tmp[i].x + tmp[i].y * tmp[i].y, m);
+                }
+            } else
             for (int m = t; m < N; m += C::T) {
                 const float2 x = slot[m];
                 sp[m + (m >> PADSHIFT)] = x;
@@ -205,7 +229,7 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
             }
             if (lane == 0) { sh.redv[warp] = best; sh.redi[warp] = besti; }
             __syncthreads();
-            if (p.use_tma && t == 0) {
+            if (!IPB && p.use_tma && t == 0) {
                 const long long nv = vox + gridDim.x;
                 if (nv < p.batch) {
                     fence_proxy_async_smem();
@@ -792,6 +816,13 @@ k2_acme_kernel(const __grid_constant__ K2Params p) {
             }
         }
         __syncthreads();   // sp (exchange B) and the shared search state are rewritten by the next voxel
+        if (IPB && p.use_tma && t == 0) {                      // one buffer: the next FID can only land now
+            const long long nv = vox + gridDim.x;
+            if (nv < p.batch) {
+                fence_proxy_async_smem();
+                issue(nv);
+            }
+        }
     }
 }
 
