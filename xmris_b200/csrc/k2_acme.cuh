@@ -39,23 +39,6 @@ constexpr float K2A_L2_DP1 = 15.f;   // L2 rows: cell.p1 + {-15, 0, 15}
 constexpr float K2A_L2_DP0 = 2.5f;   // L2 p0 candidates: cell.p0 + (k - 3.5) * 2.5
 constexpr float K2A_SIBLING = 20.f;  // sibling starts: result.p1 -+ 20 deg
 
-template <int N>
-struct K2aSmem {
-    using C = FftCfg<N>;
-    static constexpr int PADSHIFT = ilog2(N / 32 > 0 ? N / 32 : 1);
-    // N >= 8192: ONE buffer is TMA landing slot, both FFT exchanges (in place, as K1 does at this length) and then the padded
-    // spectrum the search walks: 92 KB per CTA instead of 156 KB, so that TWO CTAs fit on an SM (four instead of two warps per
-    // SM sub-partition for a latency-bound search); the next voxel's FID is fetched at the end of the voxel.
-    static constexpr bool IPB = (N >= 8192);
-    static constexpr size_t SLOT = IPB ? 0 : size_t(C::N) * sizeof(float2);
-    static constexpr size_t SPN = (size_t(C::N) + (size_t(C::N) >> PADSHIFT) + 2);
-    static constexpr size_t B = (C::SIZE_B > SPN ? size_t(C::SIZE_B) : SPN) * sizeof(float2);
-    static constexpr size_t DEC = size_t(4) * K2A_GSTRIDE * sizeof(float2);     // block moments G_1, G_2, G_3, G_5
-    static constexpr size_t ROWS = size_t(192) * 2 * sizeof(float);
-    static constexpr size_t MISC = 12288;
-    static constexpr size_t TOTAL = SLOT + B + DEC + ROWS + MISC;
-};
-
 struct K2aShared {      // lives in the MISC area
     uint64_t bar;
     float redv[32];
@@ -75,7 +58,24 @@ struct K2aShared {      // lives in the MISC area
     float zc0, zc1, zcf;
     int wall;
 };
-static_assert(sizeof(K2aShared) <= 12288, "K2aShared must fit the MISC area");
+
+template <int N>
+struct K2aSmem {
+    using C = FftCfg<N>;
+    static constexpr int PADSHIFT = ilog2(N / 32 > 0 ? N / 32 : 1);
+    // N >= 8192: ONE buffer is TMA landing slot, both FFT exchanges (in place, as K1 does at this length) and then the padded
+    // spectrum the search walks: 92 KB per CTA instead of 156 KB, so that TWO CTAs fit on an SM (four instead of two warps per
+    // SM sub-partition for a latency-bound search); the next voxel's FID is fetched at the end of the voxel.
+    static constexpr bool IPB = (N >= 8192);
+    static constexpr size_t SLOT = IPB ? 0 : size_t(C::N) * sizeof(float2);
+    static constexpr size_t SPN = (size_t(C::N) + (size_t(C::N) >> PADSHIFT) + 2);
+    static constexpr size_t B = (C::SIZE_B > SPN ? size_t(C::SIZE_B) : SPN) * sizeof(float2);
+    static constexpr size_t DEC = size_t(4) * K2A_GSTRIDE * sizeof(float2);     // block moments G_1, G_2, G_3, G_5
+    static constexpr size_t ROWS = size_t(192) * 2 * sizeof(float);
+    static constexpr size_t MISC = (sizeof(K2aShared) + 255) & ~size_t(255);
+    static constexpr size_t TOTAL = SLOT + B + DEC + ROWS + MISC;
+};
+
 
 template <int N>
 __global__ void __launch_bounds__(FftCfg<N>::T, (FftCfg<N>::T >= 256 ? 2 : (FftCfg<N>::T >= 128 ? 4 : 8)))
