@@ -118,6 +118,42 @@ def test_autophase_mode_all_accessor():
         assert abs(o2.coords["phase_p0"].values[r, 0] - i["p0"]) < ANG
 
 
+def test_mode_all_at_8192_points_spectrum_and_fid_input():
+    """N = 8192: one shared buffer is landing slot, FFT exchanges and searched spectrum (two CTAs per SM).  Spectrum input
+    (padded layout written over the buffer the spectrum landed in) and FID input (4096 -> 8192 fused chain): every voxel's own
+    pivot, the output equal to the reference's phase() at the GPU's angles, both entry points in the same valley, and the
+    objective not worse than the reference optimiser's on a sample of voxels."""
+    import xmris_b200
+    from xmris_b200.synth import make_fids_numpy
+
+    nvox, n_in, n_out = 301, 4096, 8192          # more voxels than resident CTAs: the end-of-voxel prefetch is exercised
+    fid, t, _ = make_fids_numpy("1H", nvox, n_in, seed=81)
+    da = xmris_b200.xr.DataArray(fid, dims=["voxel", "time"], coords={"time": t})
+    sp = da.xmr.zero_fill(target_points=n_out).xmr.apodize_exp(lb=5.0).xmr.to_spectrum()
+    out = sp.xmr.autophase(mode="all")
+    freqs = sp.coords["frequency"].values
+    p0, p1, piv = (out.coords[k].values for k in ("phase_p0", "phase_p1", "phase_pivot"))
+    spv = sp.values
+    for v in range(0, nvox, 7):
+        s = spv[v].astype(np.complex128)
+        assert piv[v] == freqs[int(np.argmax(np.abs(s)))]
+        same, _ = orc.phase(s, 0, freqs, p0[v], p1[v], piv[v])
+        assert rel_l2(out.values[v], same) < TOL
+    fused = da.xmr.process_fid(target_points=n_out, lb=5.0, autophase_kwargs=dict(mode="all"))
+    np.testing.assert_array_equal(fused.coords["phase_pivot"].values, piv)
+    d0 = np.abs(fused.coords["phase_p0"].values - p0)
+    d0 = np.minimum(d0, 360.0 - d0)
+    assert np.mean((d0 < 0.5) & (np.abs(fused.coords["phase_p1"].values - p1) < 1.5)) > 0.97
+    n_worse = 0
+    for v in range(0, nvox, 60):
+        s = spv[v].astype(np.complex128)
+        _, info = orc.autophase(s, 0, freqs, peak_width=100)
+        f_gpu = orc.acme_score([p0[v], p1[v]], s, freqs, piv[v])
+        f_ref = orc.acme_score([info["p0"], info["p1"]], s, freqs, info["pivot"])
+        n_worse += int(f_gpu > f_ref * (1.0 + 1e-4) + 1e-12)
+    assert n_worse <= 1
+
+
 @pytest.mark.parametrize("variant", ["p0_only", "target_coord"])
 def test_mode_all_acme_variants_against_per_spectrum_reference(variant):
     """K2-ACME with ``p0_only=True`` (one-parameter search, p1 = 0) and with ``target_coord`` (fixed, off-grid pivot for every
