@@ -94,7 +94,9 @@ __device__ __forceinline__ void amax_combine(float& v, int& i, float ov, int oi)
 //            padding, no input rotation, out_shift == N/2, with the epilogue fixed at compile time (bit mask of
 //            K1_FAST_*): no per-element predicates or index arithmetic.
 enum : int { K1_FAST_ON = 1, K1_FAST_STORE = 2, K1_FAST_STATS = 4, K1_FAST_PHASE = 8, K1_FAST_ZF2 = 16, K1_FAST_ZF4 = 32,
-             K1_FAST_PHDEV = 64 /* store+phase variants: phase parameters read from p.ph_dev (shared-memory table) */ };
+             K1_FAST_PHDEV = 64 /* store+phase variants: phase parameters read from p.ph_dev (shared-memory table) */,
+             K1_FAST_BULKST = 128 /* in-place-B store variants: results staged in the (free) shared buffer and written by ONE
+                                     cp.async.bulk per spectrum instead of 32 STG per thread (p.out 16-byte aligned) */ };
 
 // PRUNE (generic statistics-only launches with p.run_max2 set): branch and bound on the level-0 bound of k1_max.cuh,
 //            |X| <= sum_n |x_n w_n|, for ANY geometry (zero-filled input, N = 8192, table windows): a tile whose spectra
@@ -128,6 +130,8 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS * GROUPS, k1_min_blocks<N, 
     // Without the table E2 rides on the two bases of the stage-1 power chain in the same way.
     constexpr bool FOLD = F && ((FAST & K1_FAST_PHASE) != 0) && C::R0 > 1 && C::R1 > 1;
     constexpr bool IPB = KS::INPLACE_B;
+    constexpr bool BULKST = F && (FAST & K1_FAST_BULKST) != 0;
+    static_assert(!BULKST || (IPB && TMA && (FAST & K1_FAST_STORE) != 0 && C::SPB == 1), "bulk-store variants: one spectrum per tile, in-place B");
     constexpr int STAGES = KS::STAGES;
     constexpr size_t SLOT = KS::SLOT;
 
@@ -373,7 +377,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS * GROUPS, k1_min_blocks<N, 
         stage2<C, INVERSE>(t, my_B, v);
         if (IPB) {
             bsync();                       // the shared buffer is free once every thread holds its results
-            if (TMA && tid == 0) {
+            if (!BULKST && TMA && tid == 0) {
                 const long long nt = tile + (long long)STAGES * gridDim.x;
                 if (nt < ntiles) {
                     fence_proxy_async_smem();
@@ -430,7 +434,32 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS * GROUPS, k1_min_blocks<N, 
                 if (PRUNE) atomicMax(reinterpret_cast<int*>(p.run_max2), __float_as_int(best));
             }
         }
-        if (do_store && valid) {
+        if (BULKST) {
+            // stage the spectrum (final order) in the free shared buffer; ONE bulk copy writes it (32 STG per thread in a burst
+            // were 18 % of this kernel's stall samples, profiles/k1_8192_full_r2.md), and the buffer is re-armed with the next
+            // load as soon as the copy engine has read it
+            float2* stg = my_slot;
+#pragma unroll
+            for (int j = 0; j < C::C2; ++j)
+#pragma unroll
+                for (int d = 0; d < C::R2; ++d) {
+                    constexpr int NH = C::N / 2;
+                    const int kc = C::T * j + Q * d;
+                    const int m = t + (kc >= NH ? kc - NH : kc + NH);
+                    float2 x = v[j * C::R2 + d];
+                    if (FOLD) x = cmul(x, PHDEV ? ph_tab[16 + d] : p.ph_fold[d]);
+                    stg[m] = x;
+                }
+            bsync();
+            if (tid == 0) {
+                fence_proxy_async_smem();
+                bulk_s2g(p.out + spec * (long long)C::N, stg, uint32_t(C::N) * 8u);
+                bulk_commit();
+                bulk_wait_read<0>();
+                const long long nt = tile + (long long)STAGES * gridDim.x;
+                if (nt < ntiles) issue(nt, slot, (it + STAGES) % NBAR);
+            }
+        } else if (do_store && valid) {
             float2* dst = p.out + spec * (long long)C::N;
 #pragma unroll
             for (int j = 0; j < C::C2; ++j)
@@ -454,6 +483,7 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS * GROUPS, k1_min_blocks<N, 
                 }
         }
     }
+    if (BULKST && tid == 0) bulk_wait_all<0>();
 }
 
 }  // namespace xmr

@@ -44,15 +44,27 @@ static cudaError_t launch_impl(const K1Params& p, int max_ctas, cudaStream_t st)
 
 template <int N, bool INVERSE, int WIN, bool TMA, int FAST = 0, bool PRUNE = false>
 static cudaError_t launch_one(const K1Params& p, int max_ctas, cudaStream_t st) {
-    // (input a quarter of the transform: nothing to prefetch, and two separate CTAs drift into opposite phases -- measured faster)
-    if constexpr (N >= 8192 && TMA && (FAST & K1_FAST_ZF4) == 0) {
+    if constexpr (N >= 8192 && TMA) {
+        // store variants: results staged in the free shared buffer and written by one bulk copy per spectrum (16-byte aligned
+        // output; XMR_K1_BULKST=0 keeps the per-thread stores)
+        constexpr bool CAN_BULK = (FAST & K1_FAST_STORE) != 0 && (FAST & K1_FAST_STATS) == 0;
+        static const bool bulk_on = !(getenv("XMR_K1_BULKST") != nullptr && getenv("XMR_K1_BULKST")[0] == '0');
+        const bool bulk = CAN_BULK && bulk_on && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
         // two 256-thread groups per CTA sharing a three-buffer ring (K1Smem); XMR_K1_GROUPS=1 selects the two-CTA form
         static const bool grouped = !(getenv("XMR_K1_GROUPS") != nullptr && getenv("XMR_K1_GROUPS")[0] == '1');
         if (grouped) {
             // (ntiles here counts spectra: SPB == 1; one CTA takes two tiles at a time)
-            return launch_impl<N, INVERSE, WIN, TMA, FAST, PRUNE, 2>(p, max_ctas > 0 ? (max_ctas + 1) / 2 : 0, st);
+            const int mc = max_ctas > 0 ? (max_ctas + 1) / 2 : 0;
+            if constexpr (CAN_BULK) {
+                if (bulk) return launch_impl<N, INVERSE, WIN, TMA, FAST | K1_FAST_BULKST, PRUNE, 2>(p, mc, st);
+            }
+            // per-thread stores with input a quarter of the transform: nothing to prefetch, and two separate CTAs drift into
+            // opposite phases -- measured faster than the grouped form
+            if constexpr ((FAST & K1_FAST_ZF4) == 0) return launch_impl<N, INVERSE, WIN, TMA, FAST, PRUNE, 2>(p, mc, st);
         }
     }
+    // (up to 4096 points -- separate exchange buffers, two barriers per tile -- the bulk store needs two more barriers and
+    //  measured slower: C5 pass 2 12.1-12.5 ms against 11.4-11.9 ms; profiles/rejected_r2.md)
     return launch_impl<N, INVERSE, WIN, TMA, FAST, PRUNE, 1>(p, max_ctas, st);
 }
 
