@@ -447,7 +447,12 @@ __global__ void __launch_bounds__(FftCfg<N>::THREADS * GROUPS, k1_min_blocks<N, 
                     const int kc = C::T * j + Q * d;
                     const int m = t + (kc >= NH ? kc - NH : kc + NH);
                     float2 x = v[j * C::R2 + d];
-                    if (FOLD) x = cmul(x, PHDEV ? ph_tab[16 + d] : p.ph_fold[d]);
+                    if (FOLD) {
+                        // explicit rounding order: the host-parameter and the device-parameter variants must agree bit for bit
+                        // (left to the compiler, the two instantiations contract this product differently)
+                        const float2 w = PHDEV ? ph_tab[16 + d] : p.ph_fold[d];
+                        x = make_float2(fmaf(x.x, w.x, -__fmul_rn(x.y, w.y)), fmaf(x.x, w.y, __fmul_rn(x.y, w.x)));
+                    }
                     stg[m] = x;
                 }
             bsync();
